@@ -1,0 +1,267 @@
+/*
+ * vattn_b200.h -- C ABI of the B200-native vAttention hot path.
+ *
+ * One shared library (libvattn_b200.so) exports everything below with C linkage,
+ * plain pointers and sizes only (no torch / ATen / pybind types).  It is what a
+ * maintainer of the reference would bind from its own extension layer:
+ *
+ *   part A  KV-cache allocator  -> replaces vattention/apis.h:1-63 (the 13 pybind
+ *           names registered at vattention/vattention.cu:614-637) and the VMM
+ *           backend in vattention/cudaInternal.h:15-94, vtensor.h:21-46.
+ *   part B  attention operators -> replaces the third-party kernels the sarathi
+ *           wrappers dispatch to:
+ *             flash_attn_with_kvcache        vattention_flashattention_wrapper.py:159-166,194-205
+ *             single_prefill_with_kv_cache   vattention_flashinfer_wrapper.py:151-158
+ *             true_fused_attn_with_kvcache   vattention_flashattention_pod_wrapper.py:177-191
+ *                                            (pod_attn/pod_attn/fused_attn_interface.py:12-137)
+ *             cache_flat                     sarathi-lean/csrc/cache_kernels.cu:524-570
+ *
+ * Conventions
+ *   - every entry point that can fail returns an int status: 0 = ok, < 0 = error;
+ *     vattn_last_error() returns the message of the last failure on the calling
+ *     thread (the text a Python binding should raise as RuntimeError).
+ *   - device pointers are raw CUDA virtual addresses; strides are in ELEMENTS;
+ *     the innermost (head_dim) dimension must be contiguous, exactly as the
+ *     reference requires (fused_attn_interface.py:80-81).
+ *   - `stream` is a CUstream / cudaStream_t passed as void*; NULL = legacy default.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef VATTN_B200_H_
+#define VATTN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VATTN_OK 0
+#define VATTN_ERR_INVALID (-1)  /* bad argument / bad configuration            */
+#define VATTN_ERR_OOM (-2)      /* "OOM on demand" / "page pool is empty"       */
+#define VATTN_ERR_DRIVER (-3)   /* a CUDA driver / runtime call failed          */
+#define VATTN_ERR_STATE (-4)    /* call sequence error (e.g. not initialised)   */
+#define VATTN_ERR_UNSUPPORTED (-5)
+
+/* message of the last failure on this thread ("" if none) */
+const char* vattn_last_error(void);
+/* library version string, e.g. "vattn_b200 0.1 (sm_100a)" */
+const char* vattn_version(void);
+
+/* ------------------------------------------------------------------------ */
+/* Part A: virtually-contiguous KV-cache allocator                           */
+/* ------------------------------------------------------------------------ */
+
+typedef struct vattn_allocator vattn_allocator_t; /* opaque */
+
+/* VMM backends.  CUDA = cuMemAddressReserve/cuMemCreate/cuMemMap through
+ * libcuda (resolved at run time, so the library loads on a box without a
+ * driver).  HOST_MOCK = same bookkeeping against a recording fake driver (no
+ * GPU); exists so the page-map arithmetic can be checked bit-exactly on CPU.
+ * It never backs a tensor that a kernel touches. */
+#define VATTN_BACKEND_CUDA 0
+#define VATTN_BACKEND_HOST_MOCK 1
+
+int vattn_create(vattn_allocator_t** out, int backend);
+int vattn_destroy(vattn_allocator_t* a);
+
+/* Derived configuration (vattention/vattention.cu:38-74 arithmetic). */
+typedef struct {
+  uint64_t num_layers, num_kv_heads, head_size, max_batch_size, max_context_length;
+  uint64_t bytes_per_elem, page_size, megacache;
+  uint64_t tokens_per_page;          /* vattention.cu:41-44   */
+  uint64_t virt_buff_size_per_token; /* vattention.cu:53-56   */
+  uint64_t virt_buff_size_per_req;   /* vattention.cu:57-67   */
+  uint64_t virt_buff_size;           /* vattention.cu:69      */
+  uint64_t max_pages_per_req;        /* vattention.cu:60      */
+  uint64_t phys_granularity;         /* what the driver reported */
+  uint64_t num_tensors;              /* 2*L, or 2 with megacache */
+} vattn_config_t;
+
+/* apis.h:3-13 init_kvcache.  Reserves VA only.  On return ptrs[0..n) holds the
+ * base device address of [K_0..K_{L-1}, V_0..V_{L-1}] (or [K, V] with
+ * megacache) -- the order of the tensor list the reference returns
+ * (vattention.cu:163-186).  `ptrs` must have room for 2*num_layers entries.
+ * shape/ndim describe one tensor: {B, maxlen, Hkv, D} or {B, maxlen, L, Hkv, D};
+ * strides are contiguous (vtensor.h:101-102).  page_size must be a multiple of
+ * the device's minimum VMM granularity (2 MiB on B200).                      */
+int vattn_init_kvcache(vattn_allocator_t* a, uint64_t num_layers, uint64_t num_kv_heads,
+                       uint64_t head_size, uint64_t max_batch_size,
+                       uint64_t max_context_length, int device, uint64_t bytes_per_elem,
+                       uint64_t page_size, int megacache, uint64_t* ptrs, int* n_ptrs,
+                       int64_t shape[5], int* ndim);
+int vattn_get_config(vattn_allocator_t* a, vattn_config_t* out);
+
+/* apis.h:23-25 reserve_physical_pages: pre-creates free_memory/page_size handles
+ * rounded down to a multiple of 2*L (utils.h:221-228); returns the pool size,
+ * or < 0 on error.                                                            */
+int64_t vattn_reserve_physical_pages(vattn_allocator_t* a, uint64_t free_memory);
+
+/* apis.h:27-29 step (all mapping on the critical path). seq_lens has n ==
+ * max_batch_size entries; 0 marks an inactive slot.                           */
+int vattn_step(vattn_allocator_t* a, const uint64_t* seq_lens, size_t n, int eager_reclaim);
+/* apis.h:31-35 step_async: maps what THIS step needs before returning, then
+ * hands "what step+1 .. step+9 will need" to the persistent mapper thread.   */
+int vattn_step_async(vattn_allocator_t* a, const uint64_t* seq_lens, size_t n);
+/* apis.h:53-59 */
+int vattn_alloc_new_batch_idx(vattn_allocator_t* a, uint64_t seqlen); /* reqId, or -1 */
+int vattn_free_batch_idx(vattn_allocator_t* a, int req_id);
+/* apis.h:61-63 */
+uint64_t vattn_num_free_kvblocks(vattn_allocator_t* a);
+/* apis.h:41-43: unmap everything, free VA, release handles */
+int vattn_cleanup(vattn_allocator_t* a);
+/* apis.h:37-39, 45-47, 15-21 */
+void vattn_set_verbose(vattn_allocator_t* a, int on);
+void vattn_set_deferred_reclamation(vattn_allocator_t* a, int on);
+void vattn_show_kvcache_config(vattn_allocator_t* a);
+void vattn_show_allocator_state(vattn_allocator_t* a);
+/* apis.h:49-51 map_common_pages (prefix-sharing proof of concept) */
+int vattn_map_common_pages(vattn_allocator_t* a, uint64_t num_tokens);
+
+/* --- B200-native additions (no reference equivalent) --- */
+/* Block until the mapper thread is idle (the reference spins on an atomic at
+ * the top of the NEXT step_async, utils.h:160-164).                          */
+int vattn_wait_background(vattn_allocator_t* a);
+/* Register the stream attention kernels run on.  Before any cuMemUnmap the
+ * allocator waits for an event recorded on this stream at the last step call,
+ * so a page is never pulled from under an in-flight kernel.  enable = 0 turns
+ * the fence off (stream NULL with enable = 1 means the legacy default stream). */
+int vattn_set_compute_stream(vattn_allocator_t* a, void* stream, int enable);
+/* Timing of the last step / background pass, nanoseconds (host clock).      */
+typedef struct {
+  uint64_t critical_path_ns;   /* time inside the last step / step_async call  */
+  uint64_t background_ns;      /* duration of the last mapper-thread pass      */
+  uint64_t sync_pages_mapped;  /* pages (not blocks) mapped on the critical path */
+  uint64_t async_pages_mapped; /* pages mapped by the last background pass     */
+  uint64_t driver_calls;       /* cumulative driver VMM calls                  */
+} vattn_step_stats_t;
+int vattn_get_step_stats(vattn_allocator_t* a, vattn_step_stats_t* out);
+
+/* --- introspection used by the parity tests --- */
+/* copies mapped_pages[] and curr_seq_lengths[] (utils.h:68-69) */
+int vattn_get_state(vattn_allocator_t* a, uint64_t* mapped_pages, uint64_t* seq_lens, size_t n);
+/* free pool, bottom -> top (the reference pops from the back, mux.h:1-8). Each
+ * id is the 0-based creation index of the handle.  Returns the pool size.    */
+size_t vattn_get_free_pool(vattn_allocator_t* a, uint64_t* ids, size_t cap);
+/* page map (utils.h:24-29), sorted by (reqId, offset, layer); 5 words per
+ * entry: reqId, req_offset, layer, k_id, v_id.  Returns the entry count.    */
+size_t vattn_get_pagemap(vattn_allocator_t* a, uint64_t* words, size_t cap_entries);
+/* HOST_MOCK only: driver-call log, 4 words per record: op, va, size, handle id
+ * (op: 1 reserve, 2 create, 3 map, 4 set_access, 5 unmap, 6 release, 7 addr_free) */
+size_t vattn_get_driver_log(vattn_allocator_t* a, uint64_t* words, size_t cap_records);
+void vattn_clear_driver_log(vattn_allocator_t* a);
+
+/* ------------------------------------------------------------------------ */
+/* Part B: attention over the contiguous K/V                                 */
+/* ------------------------------------------------------------------------ */
+
+#define VATTN_DTYPE_F16 0
+#define VATTN_DTYPE_BF16 1
+
+/* kernel selection for vattn_fwd_kvcache (0 = pick automatically) */
+#define VATTN_IMPL_AUTO 0
+#define VATTN_IMPL_SIMT 1 /* 128-bit vectorised sweep, warp-reduce softmax       */
+#define VATTN_IMPL_TC 2   /* TMA + tcgen05 (sm_100a tensor cores, TMEM)          */
+
+/*
+ * flash_attn_with_kvcache semantics (arithmetic: pod_attn/pod_attn/flash_api.cpp:1291-1580,
+ * block_info.h:11-44, mask.h:172, softmax.h:66-160, flash_fwd_kernel.h:685-790):
+ *   for b in [0,batch):  slot = cache_batch_idx ? cache_batch_idx[b] : b
+ *     L0 = cache_seqlens ? cache_seqlens[b] : seqlen_k
+ *     if k_new: rows [L0, L0+seqlen_new) of slot <- k_new[b], v_new[b]
+ *     Lk = L0 + seqlen_new
+ *     out[b,i,h] = softmax_j(scale * q[b,i,h].k[slot,j,h/g]) . v[slot,j,h/g]
+ *        over j < Lk, and when causal also j <= i + Lk - seqlen_q.
+ *     a query row with no visible key produces zeros.
+ */
+typedef struct {
+  /* q [batch, seqlen_q, num_heads, head_dim] */
+  const void* q;
+  int64_t q_batch_stride, q_row_stride, q_head_stride;
+  /* caches [cache_batch, seqlen_k, num_kv_heads, head_dim]; rows >= the mapped
+   * prefix of a slot may be unmapped VA and are never touched               */
+  void* k_cache;
+  void* v_cache;
+  int64_t k_batch_stride, k_row_stride, k_head_stride;
+  int64_t v_batch_stride, v_row_stride, v_head_stride;
+  /* optional append [batch, seqlen_new, num_kv_heads, head_dim] (NULL = none) */
+  const void* k_new;
+  const void* v_new;
+  int64_t knew_batch_stride, knew_row_stride, knew_head_stride;
+  int64_t vnew_batch_stride, vnew_row_stride, vnew_head_stride;
+  /* out [batch, seqlen_q, num_heads, head_dim] */
+  void* out;
+  int64_t o_batch_stride, o_row_stride, o_head_stride;
+  /* optional fp32 log-sum-exp [batch, num_heads, seqlen_q] (NULL = none) */
+  float* softmax_lse;
+  const int32_t* cache_seqlens;   /* [batch] or NULL */
+  const int32_t* cache_batch_idx; /* [batch] or NULL */
+  int32_t batch, cache_batch, seqlen_q, seqlen_k, seqlen_new;
+  int32_t num_heads, num_kv_heads, head_dim;
+  int32_t dtype;  /* VATTN_DTYPE_* */
+  int32_t causal; /* 0 / 1 */
+  float softmax_scale;
+  int32_t impl;       /* VATTN_IMPL_* */
+  int32_t num_splits; /* 0 = heuristic */
+  /* scratch for split-KV partials; size from vattn_fwd_kvcache_workspace().
+   * May be NULL when that returns 0.                                        */
+  void* workspace;
+  size_t workspace_bytes;
+} vattn_fwd_params_t;
+
+size_t vattn_fwd_kvcache_workspace(const vattn_fwd_params_t* p);
+int vattn_fwd_kvcache(const vattn_fwd_params_t* p, void* stream);
+
+/* flashinfer.single_prefill_with_kv_cache(q[c,Hq,D], k[n,Hkv,D], v[n,Hkv,D],
+ * causal) (vattention_flashinfer_wrapper.py:151-158): one request, NHD layout,
+ * scale = 1/sqrt(D) unless sm_scale > 0.  Strides in elements.              */
+int vattn_single_prefill(const void* q, int64_t q_row_stride, int64_t q_head_stride,
+                         const void* k, int64_t k_row_stride, int64_t k_head_stride,
+                         const void* v, int64_t v_row_stride, int64_t v_head_stride,
+                         void* out, int64_t o_row_stride, int64_t o_head_stride,
+                         int32_t qo_len, int32_t kv_len, int32_t num_heads,
+                         int32_t num_kv_heads, int32_t head_dim, int32_t dtype,
+                         int32_t causal, float sm_scale, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* POD: one launch computes a prefill problem and a decode problem
+ * (true_fused_attn_with_kvcache, fused_attn_interface.py:12-137; host
+ * fused_api.cpp:282-488).  Either side may be NULL (degenerates to the other,
+ * fused_attn_interface.py:40-78).  fused_params is accepted for signature
+ * compatibility (8/9/10/11/15/64, fused_api.cpp:24-53); scheduling here is a
+ * persistent per-SM work queue, see DESIGN.md.                              */
+size_t vattn_pod_workspace(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode);
+int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode,
+                  int32_t fused_params, void* workspace, size_t workspace_bytes, void* stream);
+
+/* cache_flat(key[c,Hkv,D], value, k_cache[>=c,Hkv,D], v_cache, "auto")
+ * (cache_kernels.cu:524-570): k_cache[t,:,:] = key[t,:,:] for t < num_tokens.
+ * Row strides in elements; each row is num_kv_heads*head_dim contiguous
+ * elements (the reference indexes i < H*D off the row base, :505-518).      */
+int vattn_cache_flat(const void* key, const void* value, void* k_cache, void* v_cache,
+                     int64_t num_tokens, int64_t row_elems, int64_t key_stride,
+                     int64_t value_stride, int64_t k_cache_stride, int64_t v_cache_stride,
+                     int32_t elem_bytes, void* stream);
+
+/* Reference-facing call with HOST buffers (bench.py's `e2e` leg): q / k_new /
+ * v_new / cache_seqlens / cache_batch_idx / out in `p` are HOST pointers
+ * (pinned for full speed); the caches stay device pointers (they are the
+ * resident state the allocator owns).  Copies in, runs vattn_fwd_kvcache,
+ * copies `out` back, all on `stream`; returns after the stream is drained.
+ * Host tensors must be densely packed ([batch, seqlen, heads, dim]).        */
+int vattn_fwd_kvcache_host(const vattn_fwd_params_t* p, void* stream);
+
+/* number of kernel launches issued by this library since load (bench.py's
+ * `gpu_launches` counts from here) */
+uint64_t vattn_launch_count(void);
+
+/* Device-side self tests of the tcgen05/TMA building blocks (used by
+ * tests/ on the GPU box): returns 0 when every variant matches the host
+ * reference, else the index (1-based) of the first failing variant; writes a
+ * human-readable report into buf.                                           */
+int vattn_selftest_umma(char* buf, size_t buf_len, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VATTN_B200_H_ */

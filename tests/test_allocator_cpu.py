@@ -1,0 +1,291 @@
+"""Allocator bookkeeping, bit-exact against the oracle (oracle/allocator_model.py), on CPU.
+
+The C++ allocator runs against the HOST_MOCK VMM driver (no GPU); the same API trace is
+replayed on the oracle; mapped_pages, seq_lens, free-pool order, page map, return values
+and num_free_kvblocks must be identical after every call.  The driver-call log is checked
+too: cuMemMap / cuMemUnmap / cuMemCreate happen in the reference's order with the
+reference's (tensor, offset, page) triples; cuMemSetAccess covers exactly what was mapped.
+"""
+import random
+
+import pytest
+import torch
+
+from oracle.allocator_model import MB, AllocatorModel, AllocatorOOM, page_size_to_block_tokens
+from vattention_b200 import _lib
+from vattention_b200 import vattention as va
+
+
+@pytest.fixture()
+def mock_backend():
+    va._use_backend(_lib.BACKEND_HOST_MOCK)
+    yield
+    va.cleanup()
+    va._use_backend(_lib.BACKEND_CUDA)
+
+
+def make_pair(L, Hkv, D, B, ctx, mega=False, mem_pages=None, itemsize=2, page=2 * MB):
+    model = AllocatorModel(L, Hkv, D, B, ctx, itemsize, page, mega)
+    dtype = {2: torch.bfloat16, 4: torch.float32}[itemsize]
+    tensors = va.init_kvcache(L, Hkv, D, B, ctx, 0, dtype, page, mega)
+    if mem_pages is not None:
+        got = va.reserve_physical_pages(mem_pages * page)
+        want = model.reserve_physical_pages(mem_pages * page)
+        assert got == want
+    return model, tensors
+
+
+def assert_same(model):
+    got = va.get_state()
+    want = model.snapshot()
+    assert got["mapped_pages"] == want["mapped_pages"]
+    assert got["seq_lens"] == want["seq_lens"]
+    assert got["pool"] == want["pool"]
+    assert got["pagemap"] == want["pagemap"]
+    assert got["num_free_kvblocks"] == want["num_free_kvblocks"]
+
+
+def test_config_arithmetic(mock_backend):
+    # Llama-3-8B shapes, SURVEY 8(a2): 2048 B/token -> 1024 tok/page, 32 pages/req at 32K
+    model, tensors = make_pair(32, 8, 128, 64, 32768)
+    cfg = va.get_config()
+    assert cfg["tokens_per_page"] == model.tokens_per_page == 1024
+    assert cfg["virt_buff_size_per_token"] == 2048
+    assert cfg["virt_buff_size_per_req"] == model.virt_buff_size_per_req == 64 * MB
+    assert cfg["max_pages_per_req"] == model.max_pages_per_req == 32
+    assert cfg["virt_buff_size"] == 4 * 1024 * MB
+    assert len(tensors) == 64 and tuple(tensors[0].shape) == (64, 32768, 8, 128)
+    # Yi-6B: 1024 B/token -> 2048 tok/page; 70B TP8: 256 B/token -> 8192 tok/page
+    assert AllocatorModel(32, 4, 128, 8, 131072, 2).tokens_per_page == 2048
+    assert AllocatorModel(80, 1, 128, 8, 131072, 2).tokens_per_page == 8192
+    # engine-side conversion (arg_utils.py:147-159)
+    assert page_size_to_block_tokens(2 * MB, 8, 128, 1, 32, False) == 1024
+    assert page_size_to_block_tokens(2 * MB, 8, 128, 8, 80, False) == 8192
+    assert page_size_to_block_tokens(2 * MB, 8, 128, 1, 32, True) == 32
+
+
+def test_megacache_geometry(mock_backend):
+    model, tensors = make_pair(4, 2, 64, 4, 16384, mega=True, mem_pages=64)
+    assert len(tensors) == 2 and tuple(tensors[0].shape) == (4, 16384, 4, 2, 64)
+    assert va.get_config()["tokens_per_page"] == model.tokens_per_page == 2 * MB // (2 * 64 * 2 * 4)
+    assert_same(model)
+
+
+def test_reserve_rounds_to_2L(mock_backend):
+    model, _ = make_pair(3, 2, 64, 4, 8192)
+    for mem in (0, 5 * MB, 12 * MB + 7, 13 * MB, 64 * MB):
+        assert va.reserve_physical_pages(mem) == model.reserve_physical_pages(mem)
+        assert_same(model)
+
+
+def test_rejects_bad_config(mock_backend):
+    with pytest.raises(RuntimeError, match="VMM granularity"):
+        va.init_kvcache(2, 2, 64, 2, 8192, 0, torch.float16, 256 * 1024, False)
+    with pytest.raises(RuntimeError, match="multiple of page_size"):
+        va.init_kvcache(2, 2, 64, 2, 1000, 0, torch.float16, 2 * MB, False)
+    with pytest.raises(RuntimeError, match="max_batch_size"):
+        va.init_kvcache(2, 2, 64, 1000, 8192, 0, torch.float16, 2 * MB, False)
+    with pytest.raises(RuntimeError, match="init_kvcache has not been called"):
+        va.step([0, 0], True)
+
+
+def test_sync_step_trace(mock_backend):
+    model, _ = make_pair(2, 2, 64, 4, 32768, mem_pages=40)
+    tpp = model.tokens_per_page
+    lens = [0, 0, 0, 0]
+    for lens in ([tpp, 0, 0, 0], [tpp + 1, 5, 0, 0], [3 * tpp, 5, 2 * tpp, 0], [3 * tpp, 0, 0, 7],
+                 [0, 0, 0, 0], [1, 1, 1, 1]):
+        va.step(lens, True)
+        model.step(lens, True)
+        assert_same(model)
+    va.step([2 * tpp, 0, 0, 0], False)
+    model.step([2 * tpp, 0, 0, 0], False)
+    assert_same(model)
+
+
+def test_oom_message_and_state(mock_backend):
+    model, _ = make_pair(2, 2, 64, 2, 32768, mem_pages=8)  # 2 KV blocks
+    tpp = model.tokens_per_page
+    with pytest.raises(RuntimeError, match="OOM on demand: not enough free pages"):
+        va.step([3 * tpp, 0], False)
+    with pytest.raises(AllocatorOOM):
+        model.step([3 * tpp, 0], False)
+    assert_same(model)
+    va.set_verbose(False)
+
+
+def test_best_fit_reqid(mock_backend):
+    model, _ = make_pair(1, 2, 64, 4, 65536, mem_pages=64)
+    tpp = model.tokens_per_page
+    for lens in ([4 * tpp, 2 * tpp, 1, 3 * tpp],):
+        va.step(lens, False)
+        model.step(lens, False)
+    for r in range(4):
+        va.free_batch_idx(r)
+        model.free_batch_idx(r)
+    # all inactive with 4,2,1,3 pages mapped: best fit picks the smallest sufficient
+    for need in (2 * tpp, 3 * tpp, 1, 10 * tpp, 5):
+        got, want = va.alloc_new_batch_idx(need), model.alloc_new_batch_idx(need)
+        assert got == want
+        assert_same(model)
+
+
+def random_trace(seed, B, ctx, tpp, steps):
+    rng = random.Random(seed)
+    lens = [0] * B
+    ops = []
+    for _ in range(steps):
+        r = rng.random()
+        active = [i for i in range(B) if lens[i]]
+        if r < 0.25 and len(active) < B:
+            n = rng.choice([1, tpp - 1, tpp, tpp + 1, 3 * tpp + 17, rng.randrange(1, ctx // 2)])
+            ops.append(("alloc", n))
+        elif r < 0.35 and active:
+            ops.append(("free", rng.choice(active)))
+        elif r < 0.40:
+            ops.append(("free_blocks",))
+        else:
+            ops.append(("step", rng.randrange(1, 4)))
+    return ops
+
+
+@pytest.mark.parametrize("mega", [False, True])
+@pytest.mark.parametrize("mode", ["async", "sync", "async_nodefer"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_traces_match_oracle(mock_backend, mega, mode, seed):
+    L, Hkv, D, B, ctx = 3, 2, 64, 6, 32768
+    model, _ = make_pair(L, Hkv, D, B, ctx, mega=mega, mem_pages=(12 if mega else 90))
+    if mode == "async_nodefer":
+        va.set_deferred_reclamation(False)
+        model.set_deferred_reclamation(False)
+    tpp = model.tokens_per_page
+    lens = [0] * B
+    rng = random.Random(100 + seed)
+    for op in random_trace(seed, B, ctx, tpp, 160):
+        if op[0] == "alloc":
+            got, want = va.alloc_new_batch_idx(op[1]), model.alloc_new_batch_idx(op[1])
+            assert got == want
+            if got >= 0:
+                lens[got] = op[1]
+        elif op[0] == "free":
+            va.free_batch_idx(op[1])
+            model.free_batch_idx(op[1])
+            lens[op[1]] = 0
+        elif op[0] == "free_blocks":
+            assert va.num_free_kvblocks() == model.num_free_kvblocks()
+        else:
+            for _ in range(op[1]):
+                for i in range(B):           # decode: every active sequence grows by one token
+                    if lens[i] and lens[i] < ctx - 1:
+                        lens[i] += rng.choice([1, 1, 1, tpp // 2])
+                        lens[i] = min(lens[i], ctx - 1)
+                err_got = err_want = None
+                try:
+                    va.step_async(lens) if mode != "sync" else va.step(lens, True)
+                except RuntimeError as e:
+                    err_got = str(e)
+                try:
+                    model.step_async(lens) if mode != "sync" else model.step(lens, True)
+                except AllocatorOOM as e:
+                    err_want = str(e)
+                assert (err_got is None) == (err_want is None)
+                if err_want:
+                    assert err_want in err_got
+                    va.set_verbose(False)
+                    # an OOM leaves both sides mid-step in the same state; drop the biggest
+                    # request on both and carry on (what the scheduler's preemption does)
+                    big = max(range(B), key=lambda i: lens[i])
+                    lens[big] = 0
+                    va.free_batch_idx(big)
+                    model.free_batch_idx(big)
+                assert_same(model)
+        assert_same(model)
+
+
+def test_driver_call_order_matches_reference(mock_backend):
+    """map/unmap/create sequence == the reference's (oracle log); set_access covers the same
+    bytes with fewer calls (one per contiguous range per tensor)."""
+    L, B = 2, 3
+    model, _ = make_pair(L, 2, 64, B, 32768, mem_pages=48)
+    cfg = va.get_config()
+    tpp, page, per_req = cfg["tokens_per_page"], cfg["page_size"], cfg["virt_buff_size_per_req"]
+    log0 = va.get_driver_log()
+    reserves = [r for r in log0 if r[0] == 1]
+    assert len(reserves) == 2 * L and all(r[2] == per_req * B for r in reserves)
+    base = {f"k{i}": reserves[i][1] for i in range(L)}
+    base.update({f"v{i}": reserves[L + i][1] for i in range(L)})
+    creates = [r for r in log0 if r[0] == 2]
+    assert [r[3] for r in creates] == list(range(1, 49))  # mock handle ids are creation order + 1
+    va.clear_driver_log()
+    model.calls.clear()
+
+    for lens in ([3 * tpp, 0, tpp], [3 * tpp + 1, 5, tpp], [0, 5, 0]):
+        va.step(lens, True)
+        model.step(lens, True)
+    got = va.get_driver_log()
+    want = model.calls
+    got_maps = [(r[1], r[3] - 1) for r in got if r[0] == 3]
+    want_maps = [(base[c.tensor] + c.offset, c.page) for c in want if c.op == "map"]
+    assert got_maps == want_maps
+    got_unmaps = [r[1] for r in got if r[0] == 5]
+    want_unmaps = [base[c.tensor] + c.offset for c in want if c.op == "unmap"]
+    assert got_unmaps == want_unmaps
+    assert all(r[2] == page for r in got if r[0] in (3, 5))
+
+    def covered(ranges):
+        s = set()
+        for va_, size in ranges:
+            s.update(range(va_, va_ + size, page))
+        return s
+    got_acc = [(r[1], r[2]) for r in got if r[0] == 4]
+    want_acc = [(base[c.tensor] + c.offset, page) for c in want if c.op == "set_access"]
+    assert covered(got_acc) == covered(want_acc)
+    assert len(got_acc) < len(want_acc)
+
+
+def test_async_eager_mapping_policy(mock_backend):
+    """The background pass maps what len+1 needs, then looks ahead up to +9 until two more
+    blocks were requested (vattention.cu:513-526)."""
+    model, _ = make_pair(1, 2, 64, 4, 32768, mem_pages=40)
+    tpp = model.tokens_per_page
+    lens = [tpp, tpp - 5, 3, 0]
+    va.step_async(lens)
+    model.step_async(lens)
+    va.wait_background()
+    assert_same(model)
+    st = va.get_state()
+    # req 0 is exactly at a page boundary -> the background pass already mapped its next page
+    assert st["mapped_pages"][0] == 2
+    # req 1 crosses within the 9-token look-ahead window -> mapped eagerly as well
+    assert st["mapped_pages"][1] == 2
+    assert st["mapped_pages"][2] == 1 and st["mapped_pages"][3] == 0
+    stats = va.get_step_stats()
+    assert stats["sync_pages_mapped"] == 2 * 3 and stats["async_pages_mapped"] == 2 * 2
+
+
+def test_map_common_pages_refcounted(mock_backend):
+    model, _ = make_pair(2, 2, 64, 3, 32768, mem_pages=24)
+    tpp = model.tokens_per_page
+    va.map_common_pages(tpp + 1)  # 2 blocks shared by all 3 requests
+    st = va.get_state()
+    assert st["mapped_pages"] == [2, 2, 2]
+    assert len(st["pool"]) == 24 - 2 * 2 * 2       # 2 blocks x 2L pages, NOT x3 requests
+    by_req = {}
+    for req, off, layer, k, v in st["pagemap"]:
+        by_req.setdefault((off % va.get_config()["virt_buff_size_per_req"], layer), set()).add((k, v))
+    assert all(len(s) == 1 for s in by_req.values())  # same physical pair under every request
+    va.step([0, 0, 0], True)                            # eager reclaim unmaps everything
+    st = va.get_state()
+    assert st["mapped_pages"] == [0, 0, 0]
+    assert sorted(st["pool"]) == list(range(24))        # every page back exactly once
+
+
+def test_cleanup_releases_everything(mock_backend):
+    model, _ = make_pair(2, 2, 64, 2, 32768, mem_pages=16)
+    va.step([model.tokens_per_page * 2, 3], False)
+    va.clear_driver_log()
+    va.cleanup()
+    # re-init works after cleanup (the reference's globals cannot do this)
+    va.init_kvcache(1, 1, 64, 1, 16384, 0, torch.float16, 2 * MB, False)
+    log = va.get_driver_log()
+    assert [r[0] for r in log].count(1) == 2

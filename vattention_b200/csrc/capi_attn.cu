@@ -1,0 +1,326 @@
+// C ABI, part B (attention operators): argument checks, kernel selection,
+// workspace sizing.  Declarations: include/vattn_b200.h.
+//
+// Why decode QK^T / PV go to tensor cores when they can (VATTN_IMPL_TC): with a GQA
+// group of g query heads every K/V byte needs 2*g FMAs (g=4: 2 FMA/B).  At the
+// measured 6.57 TB/s that is 13 TFMA/s = 46-63 FMA/clk/SM, against a CUDA-core
+// issue rate of 64 3-register FFMA/clk/SM (B300_MICROARCH.md: rt_SMSP = 2) before
+// the bf16->fp32 conversions and the shuffle reductions.  The SIMT sweep is
+// therefore instruction-bound, not HBM-bound, for g >= 2; the tcgen05 path puts
+// keys on the MMA M axis so a 32 KB K tile costs 64 tensor cycles.
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "attn_common.cuh"
+#include "capi_common.h"
+
+namespace vattn {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+void launch_cache_flat(const void*, const void*, void*, void*, int64_t, int64_t, int64_t, int64_t,
+                       int64_t, int64_t, int, cudaStream_t);
+void launch_append_kv(const vattn_fwd_params_t&, cudaStream_t);
+void launch_simt(const vattn_fwd_params_t&, int, const SplitWorkspace&, cudaStream_t);
+int simt_num_splits(const vattn_fwd_params_t&);
+// tensor-core paths (attn_decode_tc.cu / attn_prefill_tc.cu)
+bool decode_tc_supported(const vattn_fwd_params_t&, std::string* why);
+size_t decode_tc_workspace(const vattn_fwd_params_t&);
+void launch_decode_tc(const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
+bool prefill_tc_supported(const vattn_fwd_params_t&, std::string* why);
+size_t prefill_tc_workspace(const vattn_fwd_params_t&);
+void launch_prefill_tc(const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
+int run_umma_selftest(char* buf, size_t len, cudaStream_t);
+
+namespace {
+
+int translate_attn_exception() {
+  try {
+    throw;
+  } catch (const ArgError& e) {
+    g_last_error = e.what();
+    return VATTN_ERR_INVALID;
+  } catch (const UnsupportedError& e) {
+    g_last_error = e.what();
+    return VATTN_ERR_UNSUPPORTED;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return VATTN_ERR_DRIVER;
+  } catch (...) {
+    g_last_error = "unknown C++ exception";
+    return VATTN_ERR_DRIVER;
+  }
+}
+
+void validate(const vattn_fwd_params_t& p) {
+  if (!p.q || !p.k_cache || !p.v_cache || !p.out) throw ArgError("[vattn] null tensor pointer");
+  if (p.dtype != VATTN_DTYPE_F16 && p.dtype != VATTN_DTYPE_BF16)
+    throw ArgError("FlashAttention only support fp16 and bf16 data type");  // flash_api.cpp wording
+  if (p.batch < 0 || p.seqlen_q <= 0 || p.seqlen_k < 0) throw ArgError("[vattn] bad sizes");
+  if (p.num_heads <= 0 || p.num_kv_heads <= 0 || p.num_heads % p.num_kv_heads != 0)
+    throw ArgError("Number of heads in key/value must divide number of heads in query");
+  if (p.head_dim % 8 != 0) throw ArgError("head_size must be a multiple of 8");
+  if ((p.k_new == nullptr) != (p.v_new == nullptr))
+    throw ArgError("[vattn] k and v must be supplied together");
+  if (p.k_new) {
+    if (p.seqlen_new <= 0) throw ArgError("[vattn] seqlen_new must be positive when k is given");
+    // flash_api.cpp:1454 -- the sarathi wrapper pattern-matches this text
+    if (p.seqlen_new > p.seqlen_k)
+      throw ArgError("If key is supplied, it must have seqlen <= the seqlen of the KV cache");
+  }
+  auto al = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  if (!al(p.q) || !al(p.k_cache) || !al(p.v_cache) || !al(p.out) || (p.k_new && !al(p.k_new)) ||
+      (p.v_new && !al(p.v_new)))
+    throw ArgError("[vattn] tensors must be 16-byte aligned");
+  const int64_t st[] = {p.q_batch_stride, p.q_row_stride,  p.q_head_stride, p.k_batch_stride,
+                        p.k_row_stride,   p.k_head_stride, p.v_batch_stride, p.v_row_stride,
+                        p.v_head_stride,  p.o_batch_stride, p.o_row_stride,  p.o_head_stride};
+  for (int64_t s : st)
+    if (s % 8 != 0) throw ArgError("[vattn] strides must be multiples of 8 elements");
+}
+
+enum class Path { Simt, DecodeTc, PrefillTc };
+
+Path choose(const vattn_fwd_params_t& p) {
+  std::string why;
+  if (p.impl == VATTN_IMPL_SIMT) return Path::Simt;
+  const bool decode_like = p.seqlen_q == 1;
+  if (decode_like) {
+    if (decode_tc_supported(p, &why)) return Path::DecodeTc;
+  } else {
+    if (prefill_tc_supported(p, &why)) return Path::PrefillTc;
+  }
+  if (p.impl == VATTN_IMPL_TC)
+    throw UnsupportedError("[vattn] tensor-core path not available for this call: " + why);
+  return Path::Simt;
+}
+
+size_t workspace_for(const vattn_fwd_params_t& p, Path path) {
+  switch (path) {
+    case Path::DecodeTc: return decode_tc_workspace(p);
+    case Path::PrefillTc: return prefill_tc_workspace(p);
+    default: {
+      const int s = simt_num_splits(p);
+      return s > 1 ? split_workspace_bytes((int64_t)p.batch * p.seqlen_q, p.num_heads, s, p.head_dim)
+                   : 0;
+    }
+  }
+}
+
+void run_fwd(const vattn_fwd_params_t& p, cudaStream_t stream) {
+  validate(p);
+  if (p.batch == 0) return;
+  launch_append_kv(p, stream);
+  const Path path = choose(p);
+  const size_t need = workspace_for(p, path);
+  if (need > 0 && (!p.workspace || p.workspace_bytes < need))
+    throw ArgError("[vattn] workspace too small: need " + std::to_string(need) + " bytes");
+  switch (path) {
+    case Path::DecodeTc: launch_decode_tc(p, p.workspace, p.workspace_bytes, stream); break;
+    case Path::PrefillTc: launch_prefill_tc(p, p.workspace, p.workspace_bytes, stream); break;
+    default: {
+      const int s = simt_num_splits(p);
+      SplitWorkspace ws{nullptr, nullptr};
+      if (s > 1) ws = carve_workspace(p.workspace, (int64_t)p.batch * p.seqlen_q, p.num_heads, s, p.head_dim);
+      launch_simt(p, s, ws, stream);
+    }
+  }
+}
+
+// device staging arena for the host-buffer entry point
+struct HostStage {
+  void* dev = nullptr;
+  size_t cap = 0;
+  void* ws = nullptr;
+  size_t ws_cap = 0;
+  std::mutex mu;
+  void ensure(void** ptr, size_t* cap_, size_t bytes) {
+    if (*cap_ >= bytes) return;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap_ = 0;
+    VATTN_CUDA(cudaMalloc(ptr, bytes));
+    *cap_ = bytes;
+  }
+};
+HostStage g_stage;
+
+}  // namespace
+}  // namespace vattn
+
+using namespace vattn;
+
+extern "C" {
+
+size_t vattn_fwd_kvcache_workspace(const vattn_fwd_params_t* p) {
+  if (!p) return 0;
+  try {
+    validate(*p);
+    if (p->batch == 0) return 0;
+    return workspace_for(*p, choose(*p));
+  } catch (...) {
+    translate_attn_exception();
+    return 0;
+  }
+}
+
+int vattn_fwd_kvcache(const vattn_fwd_params_t* p, void* stream) {
+  if (!p) return VATTN_ERR_INVALID;
+  try {
+    run_fwd(*p, static_cast<cudaStream_t>(stream));
+    return VATTN_OK;
+  } catch (...) {
+    return translate_attn_exception();
+  }
+}
+
+int vattn_single_prefill(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                         int64_t k_row_stride, int64_t k_head_stride, const void* v,
+                         int64_t v_row_stride, int64_t v_head_stride, void* out,
+                         int64_t o_row_stride, int64_t o_head_stride, int32_t qo_len,
+                         int32_t kv_len, int32_t num_heads, int32_t num_kv_heads, int32_t head_dim,
+                         int32_t dtype, int32_t causal, float sm_scale, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  // flashinfer.single_prefill_with_kv_cache == one request, no append, the whole k/v
+  // visible, bottom-right aligned causal mask, scale 1/sqrt(D) by default
+  // (vattention_flashinfer_wrapper.py:151-158 passes no scale).
+  vattn_fwd_params_t p;
+  std::memset(&p, 0, sizeof(p));
+  p.q = q;
+  p.q_batch_stride = 0, p.q_row_stride = q_row_stride, p.q_head_stride = q_head_stride;
+  p.k_cache = const_cast<void*>(k);
+  p.v_cache = const_cast<void*>(v);
+  p.k_batch_stride = 0, p.k_row_stride = k_row_stride, p.k_head_stride = k_head_stride;
+  p.v_batch_stride = 0, p.v_row_stride = v_row_stride, p.v_head_stride = v_head_stride;
+  p.out = out;
+  p.o_batch_stride = 0, p.o_row_stride = o_row_stride, p.o_head_stride = o_head_stride;
+  p.batch = 1, p.cache_batch = 1, p.seqlen_q = qo_len, p.seqlen_k = kv_len;
+  p.num_heads = num_heads, p.num_kv_heads = num_kv_heads, p.head_dim = head_dim;
+  p.dtype = dtype, p.causal = causal;
+  p.softmax_scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)head_dim);
+  p.workspace = workspace, p.workspace_bytes = workspace_bytes;
+  return vattn_fwd_kvcache(&p, stream);
+}
+
+size_t vattn_pod_workspace(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode) {
+  size_t a = prefill ? vattn_fwd_kvcache_workspace(prefill) : 0;
+  size_t b = decode ? vattn_fwd_kvcache_workspace(decode) : 0;
+  a = (a + 255) / 256 * 256;
+  return a + b;
+}
+
+int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode,
+                  int32_t fused_params, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)fused_params;
+  try {
+    size_t a = prefill ? vattn_fwd_kvcache_workspace(prefill) : 0;
+    a = (a + 255) / 256 * 256;
+    if (prefill) {
+      vattn_fwd_params_t p = *prefill;
+      p.workspace = workspace;
+      p.workspace_bytes = a;
+      run_fwd(p, static_cast<cudaStream_t>(stream));
+    }
+    if (decode) {
+      vattn_fwd_params_t d = *decode;
+      d.workspace = workspace ? static_cast<char*>(workspace) + a : nullptr;
+      d.workspace_bytes = workspace_bytes > a ? workspace_bytes - a : 0;
+      run_fwd(d, static_cast<cudaStream_t>(stream));
+    }
+    return VATTN_OK;
+  } catch (...) {
+    return translate_attn_exception();
+  }
+}
+
+int vattn_cache_flat(const void* key, const void* value, void* k_cache, void* v_cache,
+                     int64_t num_tokens, int64_t row_elems, int64_t key_stride,
+                     int64_t value_stride, int64_t k_cache_stride, int64_t v_cache_stride,
+                     int32_t elem_bytes, void* stream) {
+  try {
+    if (num_tokens > 0 && (!key || !value || !k_cache || !v_cache)) throw ArgError("[vattn] null tensor pointer");
+    launch_cache_flat(key, value, k_cache, v_cache, num_tokens, row_elems, key_stride, value_stride,
+                      k_cache_stride, v_cache_stride, elem_bytes, static_cast<cudaStream_t>(stream));
+    return VATTN_OK;
+  } catch (...) {
+    return translate_attn_exception();
+  }
+}
+
+int vattn_fwd_kvcache_host(const vattn_fwd_params_t* hp, void* stream_) {
+  if (!hp) return VATTN_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  try {
+    std::lock_guard<std::mutex> g(g_stage.mu);
+    const size_t eb = 2;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t q_bytes = (size_t)hp->batch * hp->seqlen_q * hp->num_heads * hp->head_dim * eb;
+    const size_t kn_bytes =
+        hp->k_new ? (size_t)hp->batch * hp->seqlen_new * hp->num_kv_heads * hp->head_dim * eb : 0;
+    const size_t idx_bytes = (size_t)hp->batch * sizeof(int32_t);
+    const size_t total = up(q_bytes) * 2 + up(kn_bytes) * 2 + up(idx_bytes) * 2;
+    g_stage.ensure(&g_stage.dev, &g_stage.cap, total);
+    char* base = static_cast<char*>(g_stage.dev);
+    char* d_q = base;
+    char* d_o = d_q + up(q_bytes);
+    char* d_kn = d_o + up(q_bytes);
+    char* d_vn = d_kn + up(kn_bytes);
+    char* d_sl = d_vn + up(kn_bytes);
+    char* d_bi = d_sl + up(idx_bytes);
+
+    vattn_fwd_params_t p = *hp;
+    VATTN_CUDA(cudaMemcpyAsync(d_q, hp->q, q_bytes, cudaMemcpyHostToDevice, stream));
+    p.q = d_q;
+    p.q_head_stride = hp->head_dim;
+    p.q_row_stride = (int64_t)hp->num_heads * hp->head_dim;
+    p.q_batch_stride = p.q_row_stride * hp->seqlen_q;
+    p.out = d_o;
+    p.o_head_stride = p.q_head_stride, p.o_row_stride = p.q_row_stride, p.o_batch_stride = p.q_batch_stride;
+    if (hp->k_new) {
+      VATTN_CUDA(cudaMemcpyAsync(d_kn, hp->k_new, kn_bytes, cudaMemcpyHostToDevice, stream));
+      VATTN_CUDA(cudaMemcpyAsync(d_vn, hp->v_new, kn_bytes, cudaMemcpyHostToDevice, stream));
+      p.k_new = d_kn, p.v_new = d_vn;
+      p.knew_head_stride = p.vnew_head_stride = hp->head_dim;
+      p.knew_row_stride = p.vnew_row_stride = (int64_t)hp->num_kv_heads * hp->head_dim;
+      p.knew_batch_stride = p.vnew_batch_stride = p.knew_row_stride * hp->seqlen_new;
+    }
+    if (hp->cache_seqlens) {
+      VATTN_CUDA(cudaMemcpyAsync(d_sl, hp->cache_seqlens, idx_bytes, cudaMemcpyHostToDevice, stream));
+      p.cache_seqlens = reinterpret_cast<const int32_t*>(d_sl);
+    }
+    if (hp->cache_batch_idx) {
+      VATTN_CUDA(cudaMemcpyAsync(d_bi, hp->cache_batch_idx, idx_bytes, cudaMemcpyHostToDevice, stream));
+      p.cache_batch_idx = reinterpret_cast<const int32_t*>(d_bi);
+    }
+    p.softmax_lse = nullptr;
+    validate(p);
+    const size_t need = p.batch ? workspace_for(p, choose(p)) : 0;
+    if (need) g_stage.ensure(&g_stage.ws, &g_stage.ws_cap, need);
+    p.workspace = g_stage.ws;
+    p.workspace_bytes = g_stage.ws_cap;
+    run_fwd(p, stream);
+    VATTN_CUDA(cudaMemcpyAsync(hp->out, d_o, q_bytes, cudaMemcpyDeviceToHost, stream));
+    VATTN_CUDA(cudaStreamSynchronize(stream));
+    return VATTN_OK;
+  } catch (...) {
+    return translate_attn_exception();
+  }
+}
+
+uint64_t vattn_launch_count(void) { return g_launch_count.load(); }
+
+int vattn_selftest_umma(char* buf, size_t buf_len, void* stream) {
+  try {
+    return run_umma_selftest(buf, buf_len, static_cast<cudaStream_t>(stream));
+  } catch (...) {
+    translate_attn_exception();
+    if (buf && buf_len) {
+      std::strncpy(buf, g_last_error.c_str(), buf_len - 1);
+      buf[buf_len - 1] = 0;
+    }
+    return -1;
+  }
+}
+
+}  // extern "C"

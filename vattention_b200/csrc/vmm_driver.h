@@ -1,0 +1,94 @@
+// VMM driver layer: the handful of CUDA *driver* entry points the allocator
+// needs (reference: vattention/cudaInternal.h:15-94, vtensor.h:37), behind an
+// interface with two implementations:
+//   CudaVmmDriver  -- libcuda.so.1 resolved with dlopen/dlsym at first use, so
+//                     libvattn_b200.so itself loads on a machine without a
+//                     driver (the CPU test box).
+//   MockVmmDriver  -- records calls and hands out fake VAs / handle ids; lets
+//                     the bookkeeping be checked bit-exactly on CPU.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace vattn {
+
+using u64 = uint64_t;
+
+enum DriverOp : u64 {
+  OP_RESERVE = 1,
+  OP_CREATE = 2,
+  OP_MAP = 3,
+  OP_SET_ACCESS = 4,
+  OP_UNMAP = 5,
+  OP_RELEASE = 6,
+  OP_ADDR_FREE = 7,
+};
+
+struct DriverLogRecord {
+  u64 op, va, size, handle;
+};
+
+class VmmDriver {
+ public:
+  virtual ~VmmDriver() = default;
+  // cuInit + current-context check + granularity query (cudaInternal.h:15-35).
+  // Returns the minimum physical allocation granularity for `device`.
+  virtual u64 init(int device) = 0;
+  virtual u64 reserve(u64 size, u64 alignment) = 0;            // cuMemAddressReserve
+  virtual u64 create(u64 size) = 0;                             // cuMemCreate (pinned, device)
+  virtual void map(u64 va, u64 size, u64 handle) = 0;           // cuMemMap
+  virtual void set_access(u64 va, u64 size) = 0;                // cuMemSetAccess (RW, device)
+  virtual void unmap(u64 va, u64 size) = 0;                     // cuMemUnmap
+  virtual void release(u64 handle) = 0;                         // cuMemRelease
+  virtual void addr_free(u64 va, u64 size) = 0;                 // cuMemAddressFree
+  // make the allocator's context current on the calling thread (mapper thread)
+  virtual void bind_thread() = 0;
+  // fence support: record an event on `stream` / wait for it on the host
+  virtual void record_fence(void* stream) = 0;
+  virtual void wait_fence() = 0;
+  virtual bool is_mock() const = 0;
+  u64 calls() const { return calls_; }
+
+ protected:
+  u64 calls_ = 0;
+};
+
+class MockVmmDriver : public VmmDriver {
+ public:
+  explicit MockVmmDriver(u64 granularity = 2ull << 20) : gran_(granularity) {}
+  u64 init(int) override { return gran_; }
+  u64 reserve(u64 size, u64 alignment) override;
+  u64 create(u64 size) override;
+  void map(u64 va, u64 size, u64 handle) override;
+  void set_access(u64 va, u64 size) override;
+  void unmap(u64 va, u64 size) override;
+  void release(u64 handle) override;
+  void addr_free(u64 va, u64 size) override;
+  void bind_thread() override {}
+  void record_fence(void*) override {}
+  void wait_fence() override {}
+  bool is_mock() const override { return true; }
+
+  std::vector<DriverLogRecord> snapshot_log();
+  void clear_log();
+
+ private:
+  void log(u64 op, u64 va, u64 size, u64 h);
+  u64 gran_;
+  u64 next_va_ = 0x7f0000000000ull;  // fake VA space, never dereferenced
+  u64 next_handle_ = 1;
+  std::mutex mu_;
+  std::vector<DriverLogRecord> log_;
+};
+
+// Real driver. Throws std::runtime_error with the driver's error string.
+std::unique_ptr<VmmDriver> make_cuda_vmm_driver();
+
+// dlsym'd libcuda entry (shared with the TMA descriptor encoder in the kernels'
+// host code).  Returns nullptr when libcuda.so.1 or the symbol is missing.
+void* cuda_driver_symbol(const char* name);
+
+}  // namespace vattn
