@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- the vAttention hot path on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|fa_vattn]
+
+Workload (config.workload = "decode32k"): BASELINE.json configs[1] -- Llama-3-8B attention
+shapes (Hq 32, Hkv 8, D 128, 32 layers), batch 64, every sequence at 32K context, K/V in
+vAttention virtual tensors with 2 MB pages (fa_vattn_2mb).  One STEP = one decode iteration of
+the path: allocator step_async(seq_lens) + 32 layer-calls of flash_attn_with_kvcache(q[64,1],
+K, V, k_new, v_new, cache_seqlens, cache_batch_idx) (append + attention), producing 64 tokens.
+Full-model KV at this shape is 256 GiB, so (like the reference's own
+microbenchmarks/perf_pagesize/bench_pagesize.py:22) only a few layers are resident and the 32
+calls rotate over them; each call still streams its own 8.6 GB, far beyond the 126 MB L2.
+
+metric  decode tokens/s (attention path) = 64 * K / t_K_steps, device-timed, max over ranks.
+e2e     same metric through the host-buffer C-ABI call (vattn_fwd_kvcache_host): q/k/v/index
+        arrays start in pinned host memory every call and the output is read back to the host.
+roofline  dominant kernel = the decode attention sweep; algorithmic bytes per launch
+        / its average device duration, taken with CUDA events around that kernel inside the
+        timed region (vattn_kernel_timing), against the measured HBM copy bandwidth.
+N > 1   head-sharded tensor parallel: rank r owns Hq/N q heads and Hkv/N kv heads and
+        its own allocator; per layer-call the rank multiplies its attention output with its
+        o_proj shard and ONE NCCL all-reduce sums the [64, 4096] partials.  The model is fixed,
+        so per-GPU work shrinks with N: "scaling": "strong".
+--impl reference   the reference's CPU path for the same metric: torch SDPA over the same shapes
+        on the host cores (oracle/attention_ref.sdpa_decode_cpu), a bounded sample per step.
+--impl fa_vattn    (not run by the driver) flash_attn.flash_attn_with_kvcache over the same
+        virtual tensors on the same box: the reference's own GPU dispatch target.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+# Llama-3-8B attention geometry (pod_attn/tests/utils.py:32)
+HQ, HKV, D, LAYERS, HIDDEN = 32, 8, 128, 32, 4096
+BATCH, CTX = 64, 32768
+PAGE = 2 << 20
+DTYPE = torch.bfloat16
+
+
+def rank_info():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def measured_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(gpu_index), "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
+        os.unlink(self.tmp.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower() == "active":
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(lens_after_append, hq, hkv, batch) -> int:
+    """K and V read once (incl. the appended token) + Q read / O write + k/v new write."""
+    itemsize = 2
+    return (2 * itemsize * hkv * D * int(sum(lens_after_append))
+            + 2 * itemsize * batch * hq * D + 2 * itemsize * batch * hkv * D)
+
+
+# ------------------------------------------------------------------------------- ours ---
+
+def run_ours(args):
+    rank, local_rank, world = rank_info()
+    assert world == args.gpus, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from vattention_b200 import attention as att
+    from vattention_b200 import vattention as va
+    from vattention_b200.tp import HeadShard, HeadShardedAttention
+
+    shard = HeadShard(rank, world, HQ, HKV, D)
+    hq, hkv = shard.heads_per_rank, shard.kv_heads_per_rank
+    K, W = args.steps, args.warmup
+    total_steps = W + K + (W + K if not args.no_e2e else 0) + 2
+    start_len = CTX - total_steps - 1           # every sequence ends the run at <= CTX tokens
+    assert start_len > 0
+    torch.zeros(1, device=dev)                  # context for the allocator (cudaInternal.h:19-25)
+    n_res = args.resident_layers
+    tensors = va.init_kvcache(n_res, hkv, D, BATCH, CTX, local_rank, DTYPE, PAGE, False)
+    per_layer_bytes = 2 * BATCH * CTX * hkv * D * 2
+    va.reserve_physical_pages(n_res * per_layer_bytes)
+    va.set_compute_stream(torch.cuda.current_stream(dev).cuda_stream, True)
+    k_layers, v_layers = tensors[:n_res], tensors[n_res:]
+    # the serving loop's slot assignment: alloc_new_batch_idx per sequence, then a shuffled
+    # cache_batch_idx like the reference's microbenchmarks
+    rids = [va.alloc_new_batch_idx(start_len) for _ in range(BATCH)]
+    assert sorted(rids) == list(range(BATCH))
+    seq_lens = [start_len] * BATCH
+    va.step_async(seq_lens)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    for t in list(k_layers) + list(v_layers):
+        for b in range(BATCH):
+            t[b, :start_len + 8].normal_(generator=g)
+    perm = torch.randperm(BATCH, generator=torch.Generator().manual_seed(0))
+    batch_idx = perm.int().to(dev)
+    q = torch.randn(LAYERS, BATCH, 1, hq, D, device=dev, generator=g).to(DTYPE)
+    kn = torch.randn(LAYERS, BATCH, 1, hkv, D, device=dev, generator=g).to(DTYPE)
+    vn = torch.randn(LAYERS, BATCH, 1, hkv, D, device=dev, generator=g).to(DTYPE)
+    w_o = (torch.randn(hq * D, HIDDEN, device=dev, generator=g) * 0.02).to(DTYPE) if world > 1 else None
+    tp_attn = HeadShardedAttention(shard, w_o, att.flash_attn_with_kvcache) if world > 1 else None
+    scale = D ** -0.5
+    sink = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    def one_step(lens_now):
+        """lens_now: cached length per slot BEFORE this step's token."""
+        new_lens = [n + 1 for n in lens_now]
+        va.step_async(new_lens)                 # pages for this token are mapped on return
+        cache_seqlens = torch.full((BATCH,), lens_now[0], dtype=torch.int32, device=dev)
+        max_len = lens_now[0] + 1
+        for layer in range(LAYERS):
+            kc = k_layers[layer % n_res][:, :max_len]
+            vc = v_layers[layer % n_res][:, :max_len]
+            if tp_attn is None:
+                out = att.flash_attn_with_kvcache(q[layer], kc, vc, kn[layer], vn[layer],
+                                                  cache_seqlens=cache_seqlens, cache_batch_idx=batch_idx,
+                                                  softmax_scale=scale, causal=True)
+            else:
+                out = tp_attn.forward(q[layer], kc, vc, kn[layer], vn[layer], cache_seqlens=cache_seqlens,
+                                      cache_batch_idx=batch_idx, softmax_scale=scale, causal=True)
+        sink.add_(out.flatten()[0].float())
+        return new_lens
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        seq_lens = one_step(seq_lens)
+    barrier()
+    att.kernel_timing(1)
+    launches0 = att.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lens_first = seq_lens[0]
+    e0.record()
+    for _ in range(K):
+        seq_lens = one_step(seq_lens)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    kern_ms, kern_n = att.kernel_timing(2)
+    att.kernel_timing(0)
+    launches = att.launch_count() - launches0
+    alloc_stats = va.get_step_stats()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = BATCH * K / (ms / 1e3)
+
+    # roofline of the dominant kernel (per launch = one layer-call on this rank's head shard)
+    mean_len_after = lens_first + (K + 1) / 2.0
+    bytes_per_launch = algorithmic_bytes([mean_len_after] * BATCH, hq, hkv, BATCH)
+    peak, peak_src = measured_peak()
+    roof = None
+    if kern_n:
+        achieved = bytes_per_launch / (kern_ms / kern_n * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None,
+                "kernel_ms_per_launch": round(kern_ms / kern_n, 4), "launches_timed": kern_n,
+                "algorithmic_bytes_per_launch": int(bytes_per_launch), "peak_source": peak_src}
+
+    # ---- e2e: host buffers through the C ABI ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        qh = q.cpu().pin_memory()
+        knh, vnh = kn.cpu().pin_memory(), vn.cpu().pin_memory()
+        idx_h = perm.int().pin_memory()
+        outh = torch.empty(BATCH, 1, hq, D, dtype=DTYPE).pin_memory()
+        sl_h = torch.empty(BATCH, dtype=torch.int32).pin_memory()
+        pin_partial = torch.empty(BATCH, HIDDEN, dtype=DTYPE).pin_memory() if world > 1 else None
+
+        def one_step_e2e(lens_now):
+            new_lens = [n + 1 for n in lens_now]
+            va.step_async(new_lens)
+            sl_h.fill_(lens_now[0])
+            max_len = lens_now[0] + 1
+            for layer in range(LAYERS):
+                kc = k_layers[layer % n_res][:, :max_len]
+                vc = v_layers[layer % n_res][:, :max_len]
+                if world == 1:
+                    att.flash_attn_with_kvcache_host(qh[layer], kc, vc, knh[layer], vnh[layer], sl_h, idx_h,
+                                                     outh, softmax_scale=scale, causal=True)
+                else:
+                    qd = qh[layer].to(dev, non_blocking=True)
+                    knd, vnd = knh[layer].to(dev, non_blocking=True), vnh[layer].to(dev, non_blocking=True)
+                    sld, idd = sl_h.to(dev, non_blocking=True), idx_h.to(dev, non_blocking=True)
+                    part = tp_attn.forward(qd, kc, vc, knd, vnd, cache_seqlens=sld, cache_batch_idx=idd,
+                                           softmax_scale=scale, causal=True)
+                    pin_partial.copy_(part, non_blocking=True)
+                    torch.cuda.current_stream(dev).synchronize()
+            return new_lens
+
+        for _ in range(W):
+            seq_lens = one_step_e2e(seq_lens)
+        barrier()
+        e0.record()
+        for _ in range(K):
+            seq_lens = one_step_e2e(seq_lens)
+        e1.record()
+        barrier()
+        ms_e = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        h2d = LAYERS * (BATCH * hq * D * 2 + 2 * BATCH * hkv * D * 2 + 2 * BATCH * 4)
+        d2h = LAYERS * (BATCH * (HIDDEN if world > 1 else hq * D) * 2)
+        e2e = {"value": round(BATCH * K / (ms_e / 1e3), 2), "unit": "tokens/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": round(ms_e / K, 3),
+               "api": "vattn_fwd_kvcache_host (C ABI, pinned host q/k/v/idx/out)" if world == 1
+               else "pinned host -> HeadShardedAttention.forward -> pinned host"}
+
+    # ---- CPU baseline (rank 0, N == 1) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(sample_seqs=args.cpu_sample_seqs, budget_s=args.cpu_budget_s)
+
+    va.cleanup()
+    if rank == 0:
+        line = {
+            "metric": "decode tokens/s @32K ctx (Llama-3-8B attention path)", "value": round(value, 2),
+            "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 3), "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic N(0,1) q/k/v, uniform 32K lengths, shuffled cache_batch_idx",
+            "config": {"workload": "decode32k", "shapes": f"B{BATCH} Hq{HQ} Hkv{HKV} D{D} L{LAYERS} ctx{CTX}",
+                       "backend": "fa_vattn_2mb (vAttention virtual tensors, 2 MiB pages, step_async)",
+                       "resident_layers": n_res, "parallelism": f"tp{world}" if world > 1 else "single",
+                       "l2": "each layer-call streams 8.6 GB of K/V (>> 126 MB L2); no flush needed",
+                       "ms_per_layer_call": round(ms / K / LAYERS, 4)},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks,
+            "allocator": {"step_async_critical_path_us": round(alloc_stats["critical_path_ns"] / 1e3, 1),
+                          "background_pass_us": round(alloc_stats["background_ns"] / 1e3, 1)},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------- reference ---
+
+def cpu_unit_seconds(n_seqs: int, threads: int, reps: int = 1) -> float:
+    """Seconds for ONE (sequence, layer) unit of the workload on the CPU: torch SDPA decode over
+    32K keys, Llama-3-8B heads, bf16 K/V (the reference's CPU-runnable path, BASELINE configs[0]
+    scaled to configs[1]'s context)."""
+    from oracle import attention_ref as ref
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(n_seqs, 1, HQ, D, generator=g).to(DTYPE)
+    k = torch.randn(n_seqs, CTX, HKV, D, generator=g).to(DTYPE)
+    v = torch.randn(n_seqs, CTX, HKV, D, generator=g).to(DTYPE)
+    ref.sdpa_decode_cpu(q[:1], k[:1], v[:1], D ** -0.5)  # warm up the thread pool
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ref.sdpa_decode_cpu(q, k, v, D ** -0.5)
+    return (time.perf_counter() - t0) / (reps * n_seqs)
+
+
+def cpu_baseline(sample_seqs: int = 2, budget_s: float = 20.0) -> dict:
+    threads = os.cpu_count() or 1
+    t_unit = cpu_unit_seconds(sample_seqs, threads)
+    reps = max(1, min(8, int(budget_s / max(t_unit * sample_seqs, 1e-3)) - 1))
+    if reps > 1:
+        t_unit = cpu_unit_seconds(sample_seqs, threads, reps)
+    return {"value": round(1.0 / (LAYERS * t_unit), 4), "unit": "tokens/s", "cores": threads,
+            "kind": "port",
+            "sample": f"torch SDPA (CPU, bf16) on {sample_seqs} of the 64 sequences x 1 of 32 layers at "
+                      f"32K ctx, x{reps}; tokens/s = 64 / (32 layers * 64 seqs * {t_unit * 1e3:.1f} ms per seq-layer)"}
+
+
+def run_reference(args):
+    rank, _, world = rank_info()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    n = args.cpu_sample_seqs
+    for _ in range(min(W, 1)):
+        cpu_unit_seconds(n, threads)
+    t0 = time.perf_counter()
+    units = 0.0
+    for _ in range(K):
+        units += cpu_unit_seconds(n, threads) * n
+    wall = time.perf_counter() - t0
+    t_unit = units / (K * n)
+    value = 1.0 / (LAYERS * t_unit)
+    line = {"impl": "reference", "metric": "decode tokens/s @32K ctx (Llama-3-8B attention path)",
+            "value": round(value, 4), "unit": "tokens/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": round(wall / K * 1e3, 2), "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic N(0,1)",
+            "config": {"workload": "decode32k", "shapes": f"B{BATCH} Hq{HQ} Hkv{HKV} D{D} L{LAYERS} ctx{CTX}",
+                       "note": "reference CPU path: torch SDPA on host cores; each step is a bounded sample "
+                               f"of {n} (sequence, layer) units of the 64 x 32 in one decode iteration, "
+                               "extrapolated linearly"},
+            "cpu_baseline": {"value": round(value, 4), "unit": "tokens/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} seq-layer units per step, {t_unit * 1e3:.1f} ms each"},
+            "e2e": {"value": round(value, 4), "unit": "tokens/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- fa_vattn ---
+
+def run_fa_vattn(args):
+    """The reference's own GPU dispatch target on this box: flash_attn_with_kvcache (library) over the
+    same vAttention tensors.  Reported for comparison; never part of the product path."""
+    from flash_attn import flash_attn_with_kvcache
+    from vattention_b200 import vattention as va
+    dev = torch.device("cuda", 0)
+    torch.zeros(1, device=dev)
+    n_res = args.resident_layers
+    K, W = args.steps, args.warmup
+    start_len = CTX - (W + K) - 2
+    tensors = va.init_kvcache(n_res, HKV, D, BATCH, CTX, 0, DTYPE, PAGE, False)
+    va.reserve_physical_pages(n_res * 2 * BATCH * CTX * HKV * D * 2)
+    seq_lens = [start_len] * BATCH
+    va.step_async(seq_lens)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    for t in tensors:
+        for b in range(BATCH):
+            t[b, :start_len + 8].normal_(generator=g)
+    batch_idx = torch.randperm(BATCH, generator=torch.Generator().manual_seed(0)).int().to(dev)
+    q = torch.randn(LAYERS, BATCH, 1, HQ, D, device=dev, generator=g).to(DTYPE)
+    kn = torch.randn(LAYERS, BATCH, 1, HKV, D, device=dev, generator=g).to(DTYPE)
+    vn = torch.randn(LAYERS, BATCH, 1, HKV, D, device=dev, generator=g).to(DTYPE)
+
+    def one_step(lens_now):
+        new_lens = [n + 1 for n in lens_now]
+        va.step_async(new_lens)
+        sl = torch.full((BATCH,), lens_now[0], dtype=torch.int32, device=dev)
+        for layer in range(LAYERS):
+            flash_attn_with_kvcache(q[layer], tensors[layer % n_res][:, :lens_now[0] + 1],
+                                    tensors[n_res + layer % n_res][:, :lens_now[0] + 1], kn[layer], vn[layer],
+                                    cache_seqlens=sl, cache_batch_idx=batch_idx, softmax_scale=D ** -0.5,
+                                    causal=True)
+        return new_lens
+
+    for _ in range(W):
+        seq_lens = one_step(seq_lens)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        seq_lens = one_step(seq_lens)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    peak, _ = measured_peak()
+    gbps = algorithmic_bytes([seq_lens[0]] * BATCH, HQ, HKV, BATCH) / (ms / K / LAYERS * 1e-3) / 1e9
+    va.cleanup()
+    print(json.dumps({"impl": "fa_vattn (flash_attn library over vAttention tensors)",
+                      "value": round(BATCH * K / (ms / 1e3), 2), "unit": "tokens/s",
+                      "ms_per_layer_call": round(ms / K / LAYERS, 4),
+                      "approx_gbps_incl_all_kernels": round(gbps, 1), "frac_of_peak": round(gbps / peak, 4)}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "fa_vattn"])
+    ap.add_argument("--resident-layers", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample-seqs", type=int, default=2)
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.impl == "fa_vattn":
+        run_fa_vattn(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

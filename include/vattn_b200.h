@@ -255,6 +255,13 @@ int vattn_fwd_kvcache_host(const vattn_fwd_params_t* p, void* stream);
  * `gpu_launches` counts from here) */
 uint64_t vattn_launch_count(void);
 
+/* Per-launch device timing of the DOMINANT kernel of each operator call (the attention
+ * sweep itself, not the append / combine helpers), taken with CUDA events on the
+ * launching stream.  op: 1 = enable, 0 = disable and clear, 2 = read: waits for the
+ * recorded events, returns the sum of elapsed milliseconds and the number of launches
+ * since the last read, then clears.  bench.py derives `roofline.achieved` from it. */
+int vattn_kernel_timing(int op, double* total_ms, uint64_t* launches);
+
 /* Device-side self tests of the tcgen05/TMA building blocks (used by
  * tests/ on the GPU box): returns 0 when every variant matches the host
  * reference, else the index (1-based) of the first failing variant; writes a

@@ -1,0 +1,193 @@
+"""GPU: the allocator against the real CUDA VMM driver.
+
+* data written through one virtual tensor lands in physical pages and survives further growth;
+* rows beyond the mapped prefix are genuinely unmapped (the kernels must never touch them);
+* traces replayed on the real driver match the oracle bit for bit, and -- when oracle/_ref was
+  built -- the LIVE reference extension in a subprocess as well;
+* attention reads straight out of the virtual tensors.
+"""
+import glob
+import json
+import os
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import alloc_traces as T
+from oracle import attention_ref as ref
+from oracle.allocator_model import MB
+from vattention_b200 import attention as att
+from vattention_b200 import vattention as va
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(autouse=True)
+def fresh():
+    torch.zeros(1, device="cuda")  # the allocator needs torch's context (cudaInternal.h:19-25)
+    yield
+    va.cleanup()
+
+
+def test_granularity_is_2mb_and_tensors_are_virtual():
+    ts = va.init_kvcache(2, 8, 128, 4, 32768, 0, torch.bfloat16, 2 * MB, False)
+    cfg = va.get_config()
+    assert cfg["phys_granularity"] == 2 * MB
+    assert len(ts) == 4 and tuple(ts[0].shape) == (4, 32768, 8, 128)
+    assert ts[0].is_cuda and ts[0].dtype == torch.bfloat16 and ts[0].is_contiguous()
+    assert ts[0].stride(0) * 2 == cfg["virt_buff_size_per_req"]
+    free0 = torch.cuda.mem_get_info()[0]
+    assert va.reserve_physical_pages(64 * MB) == 32
+    assert free0 - torch.cuda.mem_get_info()[0] >= 60 * MB  # physical memory really reserved
+
+
+def test_write_read_through_mapped_pages_and_growth():
+    L, Hkv, D, B, ctx = 2, 8, 128, 3, 8192
+    ts = va.init_kvcache(L, Hkv, D, B, ctx, 0, torch.float16, 2 * MB, False)
+    va.reserve_physical_pages(128 * MB)
+    tpp = va.get_config()["tokens_per_page"]
+    lens = [tpp + 5, 0, 3]
+    va.step(lens, True)
+    for t_i, t in enumerate(ts):
+        t[0, : lens[0]] = float(t_i + 1)
+        t[2, : lens[2]] = float(-(t_i + 1))
+    torch.cuda.synchronize()
+    lens = [3 * tpp, 7, 3]
+    va.step(lens, True)          # growth must keep what was written (pages stay mapped)
+    for t_i, t in enumerate(ts):
+        assert torch.all(t[0, : tpp + 5] == float(t_i + 1))
+        assert torch.all(t[2, :3] == float(-(t_i + 1)))
+        t[0, tpp + 5: 3 * tpp] = 9.0
+        t[1, :7] = 5.0
+    torch.cuda.synchronize()
+    st = va.get_state()
+    assert st["mapped_pages"] == [3, 1, 1]
+    # distinct physical pages everywhere
+    ids = [p for e in st["pagemap"] for p in e[3:]]
+    assert len(ids) == len(set(ids)) == 5 * 2 * L
+
+
+def test_unmapped_rows_fault_in_a_subprocess():
+    """Touching VA beyond the mapped prefix is an illegal address, not zeros: proves the tensors
+    are virtual and that kernels must respect the mapped prefix."""
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from vattention_b200 import vattention as va\n"
+        "torch.zeros(1, device='cuda')\n"
+        "ts = va.init_kvcache(1, 8, 128, 2, 8192, 0, torch.float16, 2<<20, False)\n"
+        "va.reserve_physical_pages(16<<20)\n"
+        "va.step([10, 0], True)\n"
+        "ts[0][0, :10] = 1.0; torch.cuda.synchronize(); print('mapped ok', flush=True)\n"
+        "try:\n"
+        "    ts[0][1, :10] = 1.0; torch.cuda.synchronize(); print('NO FAULT')\n"
+        "except Exception as e:\n"
+        "    print('FAULT', type(e).__name__)\n" % str(ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "mapped ok" in r.stdout
+    assert "FAULT" in r.stdout and "NO FAULT" not in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", T.TRACE_NAMES)
+def test_traces_on_real_driver_match_oracle(name):
+    mb, pb = T.ModelBackend(), T.ProductBackend(va, torch)
+    concrete = T.expand(T.build_trace(name), mb)
+    for op in concrete:
+        pb(op)
+    T.compare_snaps(pb.snaps, mb.snaps, f"product(cuda) vs oracle [{name}]")
+
+
+@pytest.mark.parametrize("name", ["llama8b_async", "mega_async", "tight_pool_sync"])
+def test_traces_match_live_reference(name):
+    if not glob.glob(str(ROOT / "oracle" / "_ref" / "vattention_ref*.so")):
+        pytest.skip("oracle/_ref not built")
+    mb, pb = T.ModelBackend(), T.ProductBackend(va, torch)
+    concrete = T.expand(T.build_trace(name), mb)
+    with tempfile.TemporaryDirectory() as td:
+        tp, op = os.path.join(td, "t.json"), os.path.join(td, "o.json")
+        json.dump(concrete, open(tp, "w"))
+        r = subprocess.run([sys.executable, str(ROOT / "oracle" / "ref_driver.py"), tp, op],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        ref_snaps = json.load(open(op))
+    for o in concrete:
+        pb(o)
+    T.compare_snaps(pb.snaps, ref_snaps, f"product(cuda) vs LIVE reference [{name}]")
+    T.compare_snaps(mb.snaps, ref_snaps, f"oracle vs LIVE reference [{name}]")
+
+
+@pytest.mark.parametrize("mega", [False, True])
+def test_decode_attention_over_virtual_tensors(mega):
+    """The fa_vattn flow end to end: allocator -> cache_flat prefill write -> decode with append,
+    reading the virtual tensors with cache_batch_idx (wrapper.py:151-155,194-205)."""
+    L, Hkv, D, Hq, B, ctx = 2, 4, 128, 16, 6, 16384
+    dtype = torch.bfloat16
+    ts = va.init_kvcache(L, Hkv, D, B, ctx, 0, dtype, 2 * MB, mega)
+    va.reserve_physical_pages(256 * MB)
+    if mega:
+        caches = [(ts[0][:, :, i], ts[1][:, :, i]) for i in range(L)]
+    else:
+        caches = list(zip(ts[:L], ts[L:]))
+    g = torch.Generator().manual_seed(3)
+    ctx_lens = [700, 2049, 33, 1500]
+    rids = [va.alloc_new_batch_idx(n) for n in ctx_lens]
+    lens = [0] * B
+    for r, n in zip(rids, ctx_lens):
+        lens[r] = n
+    va.step_async(lens)
+    host_k = {}
+    for layer, (kc, vc) in enumerate(caches):
+        for r, n in zip(rids, ctx_lens):
+            k = torch.randn(n, Hkv, D, generator=g).to(dtype)
+            v = torch.randn(n, Hkv, D, generator=g).to(dtype)
+            host_k[(layer, r)] = (k, v)
+            att.cache_flat(k.cuda(), v.cuda(), kc[r], vc[r], "auto")
+    # one decode step: every sequence grows by one token
+    lens = [n + 1 if n else 0 for n in lens]
+    va.step_async(lens)
+    q = torch.randn(len(rids), 1, Hq, D, generator=g).to(dtype)
+    kn = torch.randn(len(rids), 1, Hkv, D, generator=g).to(dtype)
+    vn = torch.randn(len(rids), 1, Hkv, D, generator=g).to(dtype)
+    seqlens = torch.tensor(ctx_lens, dtype=torch.int32)
+    idx = torch.tensor(rids, dtype=torch.int32)
+    max_len = max(ctx_lens) + 1
+    for layer, (kc, vc) in enumerate(caches):
+        out = att.flash_attn_with_kvcache(q.cuda(), kc[:, :max_len], vc[:, :max_len], kn.cuda(), vn.cuda(),
+                                          cache_seqlens=seqlens.cuda(), cache_batch_idx=idx.cuda(), causal=True)
+        kref = torch.zeros(B, max_len, Hkv, D, dtype=dtype)
+        vref = torch.zeros(B, max_len, Hkv, D, dtype=dtype)
+        for r, n in zip(rids, ctx_lens):
+            kref[r, :n], vref[r, :n] = host_k[(layer, r)]
+        want = ref.attn_with_kvcache_ref(q, kref, vref, kn, vn, seqlens, idx, causal=True)
+        err = (out.float().cpu() - want.float()).abs().max().item()
+        assert err <= 1e-3 * want.float().abs().max().item() + 2 ** -8 * want.float().abs().max().item(), err
+        for i, (r, n) in enumerate(zip(rids, ctx_lens)):  # the appended row is in the virtual tensor
+            assert torch.equal(kc[r, n].cpu(), kn[i, 0])
+
+
+def test_async_overlap_stats_and_fence():
+    """step_async returns after the sync part; the mapper thread's work is visible in the stats and
+    the next call waits for it.  With a compute stream registered, unmaps wait on the fence."""
+    L = 8
+    va.init_kvcache(L, 8, 128, 8, 32768, 0, torch.bfloat16, 2 * MB, False)
+    va.reserve_physical_pages(2048 * MB)
+    va.set_compute_stream(torch.cuda.current_stream().cuda_stream, True)
+    tpp = va.get_config()["tokens_per_page"]
+    lens = [tpp - 1] * 4 + [0] * 4
+    va.step_async(lens)            # prefill arrivals: 4 blocks mapped on the critical path
+    s0 = va.get_step_stats()
+    assert s0["sync_pages_mapped"] == 4 * 2 * L
+    # look-ahead (+2..+9 tokens) crosses into page 2, but the pass stops after
+    # EAGER_NUM_KVBLOCKS = 2 blocks (vattention.cu:487,520-524)
+    assert s0["async_pages_mapped"] == 2 * 2 * L
+    lens = [tpp] * 4 + [0] * 4
+    va.step_async(lens)            # nothing left to do synchronously: pages were pre-mapped
+    s1 = va.get_step_stats()
+    assert s1["sync_pages_mapped"] == 0
+    assert s1["critical_path_ns"] < s0["critical_path_ns"]
+    va.step([0] * 8, True)          # eager reclaim: unmap everything behind the fence
+    assert va.get_state()["mapped_pages"] == [0] * 8

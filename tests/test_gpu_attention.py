@@ -1,0 +1,291 @@
+"""GPU parity: CUDA attention through the C ABI vs the CPU oracle (oracle/attention_ref.py).
+
+Tolerance (north_star): 1e-3 relative for bf16/fp16 outputs.  Outputs are rounded to 16-bit
+(bf16 has an 8-bit mantissa: half an ulp is 2^-9 relative), so the check is
+    |out - ref| <= 1e-3 * max|ref|  +  one output-dtype ulp of |ref|
+against the fp32 oracle, i.e. 1e-3 of the tensor's scale plus the unavoidable rounding of the
+stored result.  The reference's own assertions are allclose(atol=1e-3) on randn inputs
+(pod_attn/tests/attn_sweep.py:82-97), which this implies.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import attention_ref as ref
+from vattention_b200 import attention as att
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def close(out, want, dtype):
+    out = out.float().cpu()
+    want = want.float().cpu()
+    ulp = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11}[dtype]
+    tol = 1e-3 * want.abs().max().item() + ulp * want.abs() + 1e-6
+    err = (out - want).abs()
+    bad = err > tol
+    assert not bad.any(), f"max err {err.max().item():.3e} (tol {tol.max().item():.3e}), {int(bad.sum())} bad"
+
+
+def make_case(B, Sq, Hq, Hkv, D, Sk, dtype, seed=0, ragged=True, slots=None, new=True):
+    g = torch.Generator().manual_seed(seed)
+    slots = slots or B
+    q = torch.randn(B, Sq, Hq, D, generator=g).to(dtype)
+    kc = torch.randn(slots, Sk, Hkv, D, generator=g).to(dtype)
+    vc = torch.randn(slots, Sk, Hkv, D, generator=g).to(dtype)
+    n_new = Sq if new else 0
+    if ragged:
+        lens = torch.randint(max(1, Sk // 2), Sk - n_new + 1, (B,), generator=g).int()
+        lens[0] = Sk - n_new
+        if B > 1:
+            lens[1] = 1 if not new else 0
+    else:
+        lens = torch.full((B,), Sk - n_new, dtype=torch.int32)
+    kn = torch.randn(B, n_new, Hkv, D, generator=g).to(dtype) if new else None
+    vn = torch.randn(B, n_new, Hkv, D, generator=g).to(dtype) if new else None
+    idx = torch.randperm(slots, generator=g)[:B].int() if slots != B or B > 1 else None
+    return q, kc, vc, kn, vn, lens, idx
+
+
+def run_both(case, causal, impl="auto", scale=None, num_splits=0):
+    q, kc, vc, kn, vn, lens, idx = case
+    kc_ref, vc_ref = kc.clone(), vc.clone()
+    want = ref.attn_with_kvcache_ref(q, kc_ref, vc_ref, kn, vn, lens, idx, scale, causal)
+    d = lambda t: None if t is None else t.to(DEV)
+    kc_d, vc_d = d(kc), d(vc)
+    out = att.flash_attn_with_kvcache(d(q), kc_d, vc_d, d(kn), d(vn), cache_seqlens=d(lens),
+                                      cache_batch_idx=d(idx), softmax_scale=scale, causal=causal,
+                                      impl=impl, num_splits=num_splits)
+    torch.cuda.synchronize()
+    return out, want, (kc_d, vc_d, kc_ref, vc_ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("B,Hq,Hkv,D,Sk", [
+    (1, 8, 8, 128, 1024),     # BASELINE configs[0] shape (MHA, 1K ctx)
+    (4, 32, 8, 128, 2048),    # Llama-3-8B GQA-4
+    (3, 32, 4, 128, 777),     # Yi-6B GQA-8, ragged odd length
+    (2, 8, 1, 128, 4096),     # 70B-TP8 per-GPU shape, GQA-8 on one kv head
+    (5, 6, 2, 64, 333),       # head_dim 64, GQA-3
+    (2, 5, 5, 128, 130),      # odd head count
+])
+def test_decode_append_matches_oracle(dtype, impl, B, Hq, Hkv, D, Sk):
+    case = make_case(B, 1, Hq, Hkv, D, Sk, dtype, seed=B + Sk, slots=B + 2)
+    out, want, (kc_d, vc_d, kc_ref, vc_ref) = run_both(case, causal=True, impl=impl)
+    close(out, want, dtype)
+    # the append is part of the contract: the caches must be bit-identical afterwards
+    assert torch.equal(kc_d.cpu(), kc_ref) and torch.equal(vc_d.cpu(), vc_ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("splits", [0, 1, 3, 8])
+def test_decode_split_counts(dtype, impl, splits):
+    case = make_case(3, 1, 16, 4, 128, 1500, dtype, seed=7, slots=3)
+    out, want, _ = run_both(case, causal=False, impl=impl, num_splits=splits)
+    close(out, want, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("B,Sq,Hq,Hkv,D,Sk,new", [
+    (1, 64, 8, 2, 128, 64, False),     # first chunk: square causal
+    (1, 128, 8, 2, 128, 512, False),   # chunked prefill: 384 cached + 128 new, bottom-right mask
+    (2, 37, 4, 4, 128, 300, False),    # ragged, odd chunk
+    (1, 200, 8, 8, 64, 200, False),    # head_dim 64
+    (2, 16, 8, 2, 128, 256, True),     # multi-token append + causal
+    (1, 256, 32, 4, 128, 1024, False), # Yi-6B heads
+])
+def test_prefill_matches_oracle(dtype, impl, B, Sq, Hq, Hkv, D, Sk, new):
+    case = make_case(B, Sq, Hq, Hkv, D, Sk, dtype, seed=Sq, ragged=B > 1, new=new)
+    q, kc, vc, kn, vn, lens, idx = case
+    if not new:  # cache_seqlens is the TOTAL length incl. this chunk (wrapper.py:145-166)
+        lens = torch.clamp(lens, min=Sq)
+        case = (q, kc, vc, kn, vn, lens, idx)
+    out, want, _ = run_both(case, causal=True, impl=impl)
+    close(out, want, dtype)
+    out, want, _ = run_both(case, causal=False, impl=impl)
+    close(out, want, dtype)
+
+
+def test_fully_masked_rows_are_zero():
+    # seqlen_q > seqlen_k with causal: leading query rows see no key (softmax.h:76-78)
+    q = torch.randn(1, 8, 4, 128).bfloat16()
+    kc = torch.randn(1, 16, 4, 128).bfloat16()
+    vc = torch.randn(1, 16, 4, 128).bfloat16()
+    lens = torch.tensor([3], dtype=torch.int32)
+    want = ref.attn_with_kvcache_ref(q, kc, vc, cache_seqlens=lens, causal=True)
+    out = att.flash_attn_with_kvcache(q.to(DEV), kc.to(DEV), vc.to(DEV), cache_seqlens=lens.to(DEV),
+                                      causal=True)
+    assert torch.all(out[0, :5] == 0)
+    close(out, want, torch.bfloat16)
+
+
+def test_empty_batch_and_zero_len():
+    q = torch.randn(2, 1, 4, 128, device=DEV).half()
+    kc = torch.randn(2, 64, 4, 128, device=DEV).half()
+    lens = torch.tensor([0, 0], dtype=torch.int32, device=DEV)
+    out = att.flash_attn_with_kvcache(q, kc, kc.clone(), cache_seqlens=lens)
+    assert torch.all(out == 0)
+    out = att.flash_attn_with_kvcache(q[:0], kc, kc.clone(), cache_seqlens=lens[:0],
+                                      cache_batch_idx=lens[:0])
+    assert out.shape == (0, 1, 4, 128)
+
+
+def test_lse_output():
+    case = make_case(2, 1, 8, 2, 128, 512, torch.float16, seed=3, slots=2, new=False)
+    q, kc, vc, _, _, lens, idx = case
+    lens = torch.clamp(lens, min=1)
+    want, lse_want = ref.attn_with_kvcache_ref(q, kc, vc, cache_seqlens=lens, cache_batch_idx=idx,
+                                               return_lse=True)
+    out, lse = att.flash_attn_with_kvcache(q.to(DEV), kc.to(DEV), vc.to(DEV), cache_seqlens=lens.to(DEV),
+                                           cache_batch_idx=idx.to(DEV), return_softmax_lse=True)
+    close(out, want, torch.float16)
+    assert torch.allclose(lse.cpu(), lse_want, atol=2e-3, rtol=1e-3)
+
+
+def test_strided_views_megacache_layout():
+    """K/V arrive as views with arbitrary outer strides: the megacache slice k[:, :, layer]
+    (vATTN_cache_engine.py:58-68) and kv_cache[0][:, :max_len] (wrapper.py:197-198)."""
+    B, S, L, Hkv, D, Hq = 3, 512, 4, 2, 128, 8
+    g = torch.Generator().manual_seed(11)
+    kmega = torch.randn(B, S, L, Hkv, D, generator=g).bfloat16()
+    vmega = torch.randn(B, S, L, Hkv, D, generator=g).bfloat16()
+    q = torch.randn(B, 1, Hq, D, generator=g).bfloat16()
+    kn = torch.randn(B, 1, Hkv, D, generator=g).bfloat16()
+    vn = torch.randn(B, 1, Hkv, D, generator=g).bfloat16()
+    lens = torch.tensor([100, 300, 255], dtype=torch.int32)
+    idx = torch.tensor([2, 0, 1], dtype=torch.int32)
+    layer, max_len = 2, 301
+    kref, vref = kmega.clone(), vmega.clone()
+    want = ref.attn_with_kvcache_ref(q, kref[:, :max_len, layer], vref[:, :max_len, layer], kn, vn,
+                                     lens, idx, causal=True)
+    kd, vd = kmega.to(DEV), vmega.to(DEV)
+    out = att.flash_attn_with_kvcache(q.to(DEV), kd[:, :max_len, layer], vd[:, :max_len, layer],
+                                      kn.to(DEV), vn.to(DEV), cache_seqlens=lens.to(DEV),
+                                      cache_batch_idx=idx.to(DEV), causal=True)
+    close(out, want, torch.bfloat16)
+    assert torch.equal(kd.cpu(), kref) and torch.equal(vd.cpu(), vref)
+
+
+def test_cache_flat_and_errors():
+    g = torch.Generator().manual_seed(5)
+    for dtype in (torch.float16, torch.bfloat16, torch.float32):
+        key = torch.randn(37, 4, 128, generator=g).to(dtype)
+        val = torch.randn(37, 4, 128, generator=g).to(dtype)
+        kc = torch.zeros(100, 4, 128, dtype=dtype)
+        vc = torch.zeros(100, 4, 128, dtype=dtype)
+        kc_r, vc_r = kc.clone(), vc.clone()
+        ref.cache_flat_ref(key, val, kc_r[20:], vc_r[20:])
+        kd, vd = kc.to(DEV), vc.to(DEV)
+        att.cache_flat(key.to(DEV), val.to(DEV), kd[20:], vd[20:], "auto")
+        assert torch.equal(kd.cpu(), kc_r) and torch.equal(vd.cpu(), vc_r)
+    # odd row size -> scalar path
+    key = torch.randn(5, 3, 20, generator=g).half()
+    kd = torch.zeros(9, 3, 20, dtype=torch.half, device=DEV)
+    vd = torch.zeros(9, 3, 20, dtype=torch.half, device=DEV)
+    att.cache_flat(key.to(DEV), key.to(DEV), kd, vd, "auto")
+    assert torch.equal(kd[:5].cpu(), key) and torch.all(kd[5:] == 0)
+    with pytest.raises(RuntimeError, match="Unsupported data type of kv cache"):
+        att.cache_flat(key.to(DEV), key.to(DEV), kd, vd, "fp8")
+    att.cache_flat(key[:0].to(DEV), key[:0].to(DEV), kd, vd, "auto")  # empty is a no-op
+
+
+def test_reference_error_message_is_preserved():
+    q = torch.randn(1, 1, 4, 128, device=DEV).half()
+    kc = torch.randn(1, 4, 4, 128, device=DEV).half()
+    kn = torch.randn(1, 8, 4, 128, device=DEV).half()
+    with pytest.raises(RuntimeError, match="If key is supplied, it must have seqlen <= the seqlen of the KV cache"):
+        att.flash_attn_with_kvcache(q, kc, kc.clone(), kn, kn.clone(),
+                                    cache_seqlens=torch.zeros(1, dtype=torch.int32, device=DEV))
+    with pytest.raises(RuntimeError, match="fp16 and bf16"):
+        att.flash_attn_with_kvcache(q.float(), kc.float(), kc.float())
+
+
+def test_single_prefill_and_pod_match_oracle():
+    g = torch.Generator().manual_seed(21)
+    dtype = torch.float16
+    # flashinfer-style single prefill: chunk of 96 queries over 480 keys
+    q = torch.randn(96, 8, 128, generator=g).to(dtype)
+    k = torch.randn(480, 2, 128, generator=g).to(dtype)
+    v = torch.randn(480, 2, 128, generator=g).to(dtype)
+    want = ref.single_prefill_ref(q, k, v, causal=True)
+    out = att.single_prefill_with_kv_cache(q.to(DEV), k.to(DEV), v.to(DEV), causal=True)
+    close(out, want, dtype)
+    # POD: one prefill chunk + a decode batch, results equal the separate calls
+    Hq, Hkv, D = 8, 2, 128
+    q_p = torch.randn(1, 128, Hq, D, generator=g).to(dtype)
+    kc_p = torch.randn(1, 640, Hkv, D, generator=g).to(dtype)
+    vc_p = torch.randn(1, 640, Hkv, D, generator=g).to(dtype)
+    lens_p = torch.tensor([512], dtype=torch.int32)
+    q_d = torch.randn(6, 1, Hq, D, generator=g).to(dtype)
+    kc_d = torch.randn(8, 400, Hkv, D, generator=g).to(dtype)
+    vc_d = torch.randn(8, 400, Hkv, D, generator=g).to(dtype)
+    kn = torch.randn(6, 1, Hkv, D, generator=g).to(dtype)
+    vn = torch.randn(6, 1, Hkv, D, generator=g).to(dtype)
+    lens_d = torch.tensor([399, 17, 250, 1, 0, 128], dtype=torch.int32)
+    idx = torch.tensor([7, 0, 3, 5, 1, 2], dtype=torch.int32)
+    kc_r, vc_r = kc_d.clone(), vc_d.clone()
+    want_p, want_d = ref.pod_ref(q_p, kc_p, vc_p, q_d, kc_r, vc_r, kn, vn, lens_p, lens_d, idx, causal=True)
+    d = lambda t: t.to(DEV)
+    kd, vd = d(kc_d), d(vc_d)
+    out_p, out_d = att.true_fused_attn_with_kvcache(
+        d(q_p), d(kc_p), d(vc_p), d(q_d), kd, vd, d(kn), d(vn), causal=True,
+        cache_seqlens_p=d(lens_p), cache_seqlens_d=d(lens_d), cache_batch_idx=d(idx), fused_params=9)
+    close(out_p, want_p, dtype)
+    close(out_d, want_d, dtype)
+    assert torch.equal(kd.cpu(), kc_r)
+    # degenerate cases (fused_attn_interface.py:40-78)
+    o_p, o_d = att.true_fused_attn_with_kvcache(None, None, None, d(q_d), kd, vd, causal=True,
+                                                cache_seqlens_d=d(lens_d) + 1, cache_batch_idx=d(idx))
+    assert o_p is None and o_d.shape == q_d.shape
+
+
+def test_config2_shape_properties():
+    """BASELINE configs[1] at FULL size is too big for the CPU oracle; check size-independent
+    properties instead: (1) permuting cache slots together with cache_batch_idx leaves the
+    output unchanged, (2) attention over V == const returns that constant, (3) split-KV count
+    does not change the result beyond rounding."""
+    B, Hq, Hkv, D, S = 16, 32, 8, 128, 8192
+    g = torch.Generator(device=DEV).manual_seed(1)
+    q = torch.randn(B, 1, Hq, D, device=DEV, generator=g).bfloat16()
+    kc = torch.randn(B, S, Hkv, D, device=DEV, generator=g).bfloat16()
+    vc = torch.randn(B, S, Hkv, D, device=DEV, generator=g).bfloat16()
+    lens = torch.randint(S // 2, S, (B,), device=DEV, generator=g).int()
+    idx = torch.arange(B, device=DEV).int()
+    base = att.flash_attn_with_kvcache(q, kc, vc, cache_seqlens=lens, cache_batch_idx=idx)
+    perm = torch.randperm(B, device=DEV, generator=g)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(B, device=DEV)
+    out = att.flash_attn_with_kvcache(q, kc[perm], vc[perm], cache_seqlens=lens,
+                                      cache_batch_idx=inv.int())
+    assert torch.equal(out, base)
+    vconst = torch.full_like(vc, 0.5)
+    out = att.flash_attn_with_kvcache(q, kc, vconst, cache_seqlens=lens, cache_batch_idx=idx)
+    assert torch.allclose(out.float(), torch.full_like(out.float(), 0.5), atol=2e-3)
+    a = att.flash_attn_with_kvcache(q, kc, vc, cache_seqlens=lens, cache_batch_idx=idx, num_splits=1)
+    b = att.flash_attn_with_kvcache(q, kc, vc, cache_seqlens=lens, cache_batch_idx=idx, num_splits=7)
+    assert torch.allclose(a.float(), b.float(), atol=2e-3, rtol=1e-2)
+    # and a subsample of rows against the oracle
+    sub = [0, 5, 11]
+    want = ref.attn_with_kvcache_ref(q[sub].cpu(), kc[sub].cpu(), vc[sub].cpu(), cache_seqlens=lens[sub].cpu())
+    close(base[sub], want, torch.bfloat16)
+
+
+def test_against_flash_attn_library_if_present():
+    """The reference's own dispatch target, on identical inputs (north_star: within 1e-3 rel)."""
+    fa = pytest.importorskip("flash_attn")
+    case = make_case(4, 1, 32, 8, 128, 4096, torch.bfloat16, seed=2, slots=6)
+    q, kc, vc, kn, vn, lens, idx = [None if t is None else t.to(DEV) for t in case]
+    kc2, vc2 = kc.clone(), vc.clone()
+    try:
+        want = fa.flash_attn_with_kvcache(q, kc2, vc2, kn, vn, cache_seqlens=lens, cache_batch_idx=idx,
+                                          causal=True)
+    except Exception as e:  # library present but not runnable on this box
+        pytest.skip(f"flash_attn not runnable: {e}")
+    out = att.flash_attn_with_kvcache(q, kc, vc, kn, vn, cache_seqlens=lens, cache_batch_idx=idx, causal=True)
+    close(out, want, torch.bfloat16)
+    assert torch.equal(kc, kc2) and torch.equal(vc, vc2)

@@ -143,6 +143,8 @@ def flash_attn_with_kvcache(
         q, k_cache, v_cache, k, v, cache_seqlens, cache_batch_idx, softmax_scale)
     if out is None:
         out = torch.empty_like(q)
+    if q.shape[0] == 0:
+        return (out, None) if return_softmax_lse else out
     lse = None
     if return_softmax_lse:
         lse = torch.empty((q.shape[0], q.shape[2], q.shape[1]), dtype=torch.float32, device=q.device)
@@ -251,3 +253,30 @@ def cache_flat(key: torch.Tensor, value: torch.Tensor, k_cache: torch.Tensor,
 
 def launch_count() -> int:
     return int(lib.vattn_launch_count())
+
+
+def flash_attn_with_kvcache_host(q_host: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
+                                 k_host: Optional[torch.Tensor], v_host: Optional[torch.Tensor],
+                                 cache_seqlens_host: Optional[torch.Tensor],
+                                 cache_batch_idx_host: Optional[torch.Tensor], out_host: torch.Tensor,
+                                 softmax_scale: Optional[float] = None, causal: bool = False,
+                                 impl: str = "auto") -> torch.Tensor:
+    """Same operation with HOST (ideally pinned) q / k / v / index / out buffers and device-resident
+    caches: the library copies in, runs the kernels and copies the result back, then drains the
+    stream (vattn_fwd_kvcache_host).  This is the call bench.py's `e2e` leg times."""
+    for t in (q_host, k_host, v_host, cache_seqlens_host, cache_batch_idx_host, out_host):
+        if t is not None and (t.is_cuda or not t.is_contiguous()):
+            raise RuntimeError("host tensors must be contiguous CPU tensors")
+    if softmax_scale is None:
+        softmax_scale = q_host.shape[-1] ** (-0.5)
+    p = _fill_params(q_host, k_cache, v_cache, k_host, v_host, out_host, cache_seqlens_host,
+                     cache_batch_idx_host, softmax_scale, causal, impl, 0, None)
+    check(lib.vattn_fwd_kvcache_host(C.byref(p), _stream(k_cache.device)))
+    return out_host
+
+
+def kernel_timing(op: int):
+    """op 1 = start, 0 = stop/clear, 2 = read -> (total_ms, launches) of the dominant kernels."""
+    ms, n = C.c_double(0.0), C.c_uint64(0)
+    check(lib.vattn_kernel_timing(op, C.byref(ms), C.byref(n)))
+    return ms.value, int(n.value)

@@ -16,6 +16,10 @@ namespace vattn {
 extern std::atomic<uint64_t> g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 
+// optional per-launch timing of the dominant kernel (vattn_kernel_timing)
+int timing_begin(cudaStream_t stream);          // returns a slot (or -1 when disabled)
+void timing_end(int slot, cudaStream_t stream);
+
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };

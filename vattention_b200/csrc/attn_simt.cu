@@ -324,12 +324,14 @@ void launch_simt_t(const vattn_fwd_params_t& p, int splits, const SplitWorkspace
   sp.chunks_per_group = (sp.group + gq - 1) / gq;
   dim3 grid(splits, p.num_kv_heads * sp.chunks_per_group, p.batch * p.seqlen_q);
   dim3 block(kWarps * 32);
+  const int tslot = timing_begin(stream);
   switch (gq) {
     case 1: attn_simt_kernel<T, D, 1><<<grid, block, 0, stream>>>(sp); break;
     case 2: attn_simt_kernel<T, D, 2><<<grid, block, 0, stream>>>(sp); break;
     case 4: attn_simt_kernel<T, D, 4><<<grid, block, 0, stream>>>(sp); break;
     default: attn_simt_kernel<T, D, 8><<<grid, block, 0, stream>>>(sp); break;
   }
+  timing_end(tslot, stream);
   count_launch();
   VATTN_CUDA(cudaGetLastError());
 }

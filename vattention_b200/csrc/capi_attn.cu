@@ -33,6 +33,36 @@ size_t prefill_tc_workspace(const vattn_fwd_params_t&);
 void launch_prefill_tc(const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
 int run_umma_selftest(char* buf, size_t len, cudaStream_t);
 
+// ---- per-launch kernel timing -------------------------------------------------------
+namespace {
+struct TimingState {
+  std::mutex mu;
+  bool enabled = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;  // recycled event pairs
+  size_t used = 0;
+} g_timing;
+}  // namespace
+
+int timing_begin(cudaStream_t stream) {
+  std::lock_guard<std::mutex> g(g_timing.mu);
+  if (!g_timing.enabled) return -1;
+  if (g_timing.used == g_timing.pool.size()) {
+    cudaEvent_t a, b;
+    VATTN_CUDA(cudaEventCreate(&a));
+    VATTN_CUDA(cudaEventCreate(&b));
+    g_timing.pool.emplace_back(a, b);
+  }
+  const int slot = (int)g_timing.used++;
+  VATTN_CUDA(cudaEventRecord(g_timing.pool[slot].first, stream));
+  return slot;
+}
+
+void timing_end(int slot, cudaStream_t stream) {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> g(g_timing.mu);
+  VATTN_CUDA(cudaEventRecord(g_timing.pool[slot].second, stream));
+}
+
 namespace {
 
 int translate_attn_exception() {
@@ -309,6 +339,35 @@ int vattn_fwd_kvcache_host(const vattn_fwd_params_t* hp, void* stream_) {
 }
 
 uint64_t vattn_launch_count(void) { return g_launch_count.load(); }
+
+int vattn_kernel_timing(int op, double* total_ms, uint64_t* launches) {
+  try {
+    std::lock_guard<std::mutex> g(g_timing.mu);
+    if (op == 1) {
+      g_timing.enabled = true;
+      g_timing.used = 0;
+    } else if (op == 0) {
+      g_timing.enabled = false;
+      g_timing.used = 0;
+    } else if (op == 2) {
+      double sum = 0;
+      for (size_t i = 0; i < g_timing.used; i++) {
+        VATTN_CUDA(cudaEventSynchronize(g_timing.pool[i].second));
+        float ms = 0;
+        VATTN_CUDA(cudaEventElapsedTime(&ms, g_timing.pool[i].first, g_timing.pool[i].second));
+        sum += ms;
+      }
+      if (total_ms) *total_ms = sum;
+      if (launches) *launches = g_timing.used;
+      g_timing.used = 0;
+    } else {
+      throw ArgError("[vattn] kernel_timing: op must be 0, 1 or 2");
+    }
+    return VATTN_OK;
+  } catch (...) {
+    return translate_attn_exception();
+  }
+}
 
 int vattn_selftest_umma(char* buf, size_t buf_len, void* stream) {
   try {
