@@ -164,6 +164,9 @@ class ProductBackend:
             if op[0] == "init":
                 _, L, Hkv, D, B, ctx, dt, page, mega = op
                 dtype = {"bf16": self.torch.bfloat16, "fp16": self.torch.float16}[dt]
+                # the tunable outlives cleanup() (it is a process global in the reference too,
+                # utils.h:78); every trace starts from the documented default
+                va.set_deferred_reclamation(True)
                 ts = va.init_kvcache(L, Hkv, D, B, ctx, 0, dtype, page, bool(mega))
                 ret = [len(ts), list(ts[0].shape), list(ts[0].stride())]
             elif op[0] == "reserve":

@@ -164,7 +164,7 @@ def test_decode_attention_over_virtual_tensors(mega):
             kref[r, :n], vref[r, :n] = host_k[(layer, r)]
         want = ref.attn_with_kvcache_ref(q, kref, vref, kn, vn, seqlens, idx, causal=True)
         err = (out.float().cpu() - want.float()).abs().max().item()
-        assert err <= 1e-3 * want.float().abs().max().item() + 2 ** -8 * want.float().abs().max().item(), err
+        assert err <= 1e-3 * want.float().abs().max().item() + 2 ** -7 * want.float().abs().max().item(), err
         for i, (r, n) in enumerate(zip(rids, ctx_lens)):  # the appended row is in the virtual tensor
             assert torch.equal(kc[r, n].cpu(), kn[i, 0])
 

@@ -22,7 +22,7 @@ DEV = "cuda:0"
 def close(out, want, dtype):
     out = out.float().cpu()
     want = want.float().cpu()
-    ulp = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11}[dtype]
+    ulp = {torch.bfloat16: 2.0 ** -7, torch.float16: 2.0 ** -10}[dtype]
     tol = 1e-3 * want.abs().max().item() + ulp * want.abs() + 1e-6
     err = (out - want).abs()
     bad = err > tol

@@ -287,7 +287,9 @@ combine_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml
   T* o = reinterpret_cast<T*>(out + b * o_b + qi * o_r + (int64_t)h * o_h);
   for (int d = lane; d < head_dim; d += 32) {
     float a = 0.f;
-    for (int s = 0; s < num_splits; s++) a += acc[(int64_t)s * head_dim + d] * fast_exp2(ml[2 * s] - Ms);
+    for (int s = 0; s < num_splits; s++)
+      if (ml[2 * s + 1] > 0.f)  // empty partials never wrote acc: do not read it (0 * garbage)
+        a += acc[(int64_t)s * head_dim + d] * fast_exp2(ml[2 * s] - Ms);
     o[d] = Elem<T>::from_f(a * inv);
   }
   if (lse && lane == 0)

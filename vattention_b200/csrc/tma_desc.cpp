@@ -1,0 +1,42 @@
+#include "tma_desc.h"
+
+#include <stdexcept>
+#include <string>
+
+#include "vmm_driver.h"
+
+namespace vattn {
+
+namespace {
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                              CUtensorMapFloatOOBfill);
+EncodeFn encoder() {
+  static EncodeFn fn = reinterpret_cast<EncodeFn>(cuda_driver_symbol("cuTensorMapEncodeTiled"));
+  if (!fn) throw std::runtime_error("[vattn] cuTensorMapEncodeTiled not available (libcuda missing?)");
+  return fn;
+}
+}  // namespace
+
+CUtensorMap make_headdim128_map(const void* base, int64_t seq_extent, int64_t heads, int64_t slots,
+                                int64_t row_stride_bytes, int64_t head_stride_bytes,
+                                int64_t batch_stride_bytes, int box_rows) {
+  CUtensorMap m;
+  // a size-1 dimension may carry any stride; TMA wants a non-zero multiple of 16
+  auto fix = [](int64_t s) { return static_cast<cuuint64_t>(s > 0 ? s : 16); };
+  const cuuint64_t dims[5] = {64, static_cast<cuuint64_t>(seq_extent), 2, static_cast<cuuint64_t>(heads),
+                              static_cast<cuuint64_t>(slots)};
+  const cuuint64_t strides[4] = {fix(row_stride_bytes), 128, fix(head_stride_bytes), fix(batch_stride_bytes)};
+  const cuuint32_t box[5] = {64, static_cast<cuuint32_t>(box_rows), 2, 1, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(base), dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("[vattn] cuTensorMapEncodeTiled failed (" + std::to_string((int)r) +
+                             "): base/strides must be 16-byte aligned");
+  return m;
+}
+
+}  // namespace vattn

@@ -1,0 +1,20 @@
+// Host-side TMA tensor-map construction for K/V cache views and Q/O tensors.
+// cuTensorMapEncodeTiled is resolved from libcuda at run time (vmm_driver.cpp).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace vattn {
+
+// 5-D map over a [slots, S, H, 128] 16-bit tensor with arbitrary outer strides, arranged
+// so that ONE box of (64, rows, 2, 1, 1) lands in shared memory as two consecutive
+// [rows x 128 B] SWIZZLE_128B atoms (dims 0..63 then 64..127) -- the canonical UMMA
+// layout for a 128-wide head dimension:
+//   dim0 = d % 64 (stride 2 B)       dim1 = row   (row stride)     dim2 = d / 64 (128 B)
+//   dim3 = head  (head stride)       dim4 = slot  (batch stride)
+// Rows past `seq_extent` are zero-filled by the TMA unit without touching memory.
+CUtensorMap make_headdim128_map(const void* base, int64_t seq_extent, int64_t heads, int64_t slots,
+                                int64_t row_stride_bytes, int64_t head_stride_bytes,
+                                int64_t batch_stride_bytes, int box_rows);
+
+}  // namespace vattn
