@@ -20,10 +20,20 @@ DEV = "cuda:0"
 
 
 def close(out, want, dtype):
+    """|out - ref| <= atol * max|ref| + one output ulp of |ref_i|, ref = fp32 oracle.
+
+    fp16: atol = 1e-3 (north_star).  bf16: atol = 3e-3.  The reference algorithm rounds P to the
+    INPUT dtype before the PV product (flash_fwd_kernel.h:366-369) and so do we; with bf16's 8-bit
+    significand that is a +-2^-8 relative perturbation per term, i.e. an error with standard
+    deviation ~0.23 % of the rms output -- about 2.5e-3 of max|ref| at 4.5 sigma over ~1e5 outputs,
+    where cancellation makes |ref_i| itself tiny and the ulp term does not help.  fp16's 11 bits put
+    the same effect at 3e-4, inside 1e-3.  test_against_flash_attn_library_if_present checks that our
+    bf16 error is no larger than the library's own."""
     out = out.float().cpu()
     want = want.float().cpu()
     ulp = {torch.bfloat16: 2.0 ** -7, torch.float16: 2.0 ** -10}[dtype]
-    tol = 1e-3 * want.abs().max().item() + ulp * want.abs() + 1e-6
+    atol = {torch.bfloat16: 3e-3, torch.float16: 1e-3}[dtype]
+    tol = atol * want.abs().max().item() + ulp * want.abs() + 1e-6
     err = (out - want).abs()
     bad = err > tol
     assert not bad.any(), f"max err {err.max().item():.3e} (tol {tol.max().item():.3e}), {int(bad.sum())} bad"
@@ -289,3 +299,18 @@ def test_against_flash_attn_library_if_present():
     out = att.flash_attn_with_kvcache(q, kc, vc, kn, vn, cache_seqlens=lens, cache_batch_idx=idx, causal=True)
     close(out, want, torch.bfloat16)
     assert torch.equal(kc, kc2) and torch.equal(vc, vc2)
+    # chunked prefill, bf16: our distance to the fp32 oracle must not exceed the library's own
+    # (FlashAttention's test-suite criterion: error <= 2x a reference implementation's error)
+    g = torch.Generator().manual_seed(9)
+    qp = torch.randn(1, 512, 32, 128, generator=g).bfloat16()
+    kp = torch.randn(1, 2048, 8, 128, generator=g).bfloat16()
+    vp = torch.randn(1, 2048, 8, 128, generator=g).bfloat16()
+    lens_p = torch.tensor([2048], dtype=torch.int32)
+    exact = ref.attn_with_kvcache_ref(qp.float(), kp.float(), vp.float(), cache_seqlens=lens_p, causal=True)
+    lib = fa.flash_attn_with_kvcache(qp.to(DEV), kp.to(DEV), vp.to(DEV), cache_seqlens=lens_p.to(DEV), causal=True)
+    ours = att.flash_attn_with_kvcache(qp.to(DEV), kp.to(DEV), vp.to(DEV), cache_seqlens=lens_p.to(DEV), causal=True)
+    e_lib = (lib.float().cpu() - exact).abs().max().item()
+    e_ours = (ours.float().cpu() - exact).abs().max().item()
+    print(f"bf16 prefill max err vs fp32 oracle: ours {e_ours:.3e}, flash_attn {e_lib:.3e}")
+    assert e_ours <= 2 * e_lib + 1e-4
+    assert (ours.float() - lib.float()).abs().max().item() <= 1e-3 * exact.abs().max().item() + 2 * e_lib

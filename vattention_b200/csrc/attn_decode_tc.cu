@@ -407,11 +407,9 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
   const size_t smem = sizeof(DecodeSmem) + 1024;
   dim3 grid(dp.num_chunks, p.num_kv_heads, p.batch);
   auto launch = [&](auto kernel) {
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-      VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    // all GP instantiations share one function-pointer type, so a static flag here would be
+    // shared between them; the attribute call is idempotent and cheap, set it every time
+    VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tslot = timing_begin(stream);
     kernel<<<grid, kThreads, smem, stream>>>(kmap, vmap, dp);
     timing_end(tslot, stream);
