@@ -220,7 +220,10 @@ def run_ours(args):
     if kern_n:
         achieved = bytes_per_launch / (kern_ms / kern_n * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
+                # workload, ncu --set full capture: profiles/r1_decode_tc_ncu_raw.csv (N = 1 shapes)
+                "traffic": 8610037000 if world == 1 else None,
                 "kernel_ms_per_launch": round(kern_ms / kern_n, 4), "launches_timed": kern_n,
                 "algorithmic_bytes_per_launch": int(bytes_per_launch), "peak_source": peak_src}
 

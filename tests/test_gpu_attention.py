@@ -314,3 +314,43 @@ def test_against_flash_attn_library_if_present():
     print(f"bf16 prefill max err vs fp32 oracle: ours {e_ours:.3e}, flash_attn {e_lib:.3e}")
     assert e_ours <= 2 * e_lib + 1e-4
     assert (ours.float() - lib.float()).abs().max().item() <= 1e-3 * exact.abs().max().item() + 2 * e_lib
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_pod_fused_many_items_matches_oracle(dtype):
+    """Enough prefill row blocks and decode chunks that every persistent CTA of the fused kernel
+    runs several work items of both kinds (barrier re-initialisation, TMEM reuse, ticket order)."""
+    g = torch.Generator().manual_seed(77)
+    Hq, Hkv, D = 8, 2, 128
+    Bp, Sq, Sk = 2, 700, 1500
+    q_p = torch.randn(Bp, Sq, Hq, D, generator=g).to(dtype)
+    kc_p = torch.randn(Bp, Sk, Hkv, D, generator=g).to(dtype)
+    vc_p = torch.randn(Bp, Sk, Hkv, D, generator=g).to(dtype)
+    lens_p = torch.tensor([1500, 901], dtype=torch.int32)
+    Bd, Sd = 37, 3000
+    q_d = torch.randn(Bd, 1, Hq, D, generator=g).to(dtype)
+    kc_d = torch.randn(Bd + 3, Sd, Hkv, D, generator=g).to(dtype)
+    vc_d = torch.randn(Bd + 3, Sd, Hkv, D, generator=g).to(dtype)
+    kn = torch.randn(Bd, 1, Hkv, D, generator=g).to(dtype)
+    vn = torch.randn(Bd, 1, Hkv, D, generator=g).to(dtype)
+    lens_d = torch.randint(0, Sd - 1, (Bd,), generator=g).int()
+    lens_d[0], lens_d[1] = Sd - 1, 0
+    idx = torch.randperm(Bd + 3, generator=g)[:Bd].int()
+    kc_r, vc_r = kc_d.clone(), vc_d.clone()
+    want_p, want_d = ref.pod_ref(q_p, kc_p, vc_p, q_d, kc_r, vc_r, kn, vn, lens_p, lens_d, idx, causal=True)
+    d = lambda t: t.to(DEV)
+    kd, vd = d(kc_d), d(vc_d)
+    for _ in range(2):  # second call re-uses the zeroed ticket counter slot in the workspace
+        out_p, out_d = att.true_fused_attn_with_kvcache(
+            d(q_p), d(kc_p), d(vc_p), d(q_d), kd, vd, d(kn), d(vn), causal=True,
+            cache_seqlens_p=d(lens_p), cache_seqlens_d=d(lens_d), cache_batch_idx=d(idx), fused_params=15)
+        torch.cuda.synchronize()
+        close(out_p, want_p, dtype)
+        close(out_d, want_d, dtype)
+    assert torch.equal(kd.cpu(), kc_r) and torch.equal(vd.cpu(), vc_r)
+    # fused == the two separate calls, bit for bit (same work functions)
+    sep_p = att.flash_attn_with_kvcache(d(q_p), d(kc_p), d(vc_p), cache_seqlens=d(lens_p), causal=True)
+    sep_d = att.flash_attn_with_kvcache(d(q_d), kd, vd, cache_seqlens=d(lens_d) + 1, cache_batch_idx=d(idx),
+                                        causal=True)
+    assert torch.equal(out_p, sep_p)
+    assert torch.equal(out_d, sep_d)

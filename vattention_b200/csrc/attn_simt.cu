@@ -258,7 +258,8 @@ attn_simt_kernel(const SimtParams p) {
 }
 
 // LSE-weighted reduction of the split partials (flash_fwd_kernel.h:1115+).
-// One warp per (row, head); lanes stride over head_dim.
+// One warp per (row, head); each lane owns 4 consecutive dims (one float4 per split, loads of
+// successive splits independent of each other).
 template <typename T>
 __global__ void __launch_bounds__(128)
 combine_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml,
@@ -283,14 +284,32 @@ combine_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) L += __shfl_xor_sync(0xffffffffu, L, off);
   const float inv = (L > 0.f) ? 1.f / L : 0.f;
-  const float* acc = ws_acc + rh * num_splits * head_dim;
+  const float4* acc = reinterpret_cast<const float4*>(ws_acc + rh * num_splits * head_dim);
   T* o = reinterpret_cast<T*>(out + b * o_b + qi * o_r + (int64_t)h * o_h);
-  for (int d = lane; d < head_dim; d += 32) {
-    float a = 0.f;
-    for (int s = 0; s < num_splits; s++)
-      if (ml[2 * s + 1] > 0.f)  // empty partials never wrote acc: do not read it (0 * garbage)
-        a += acc[(int64_t)s * head_dim + d] * fast_exp2(ml[2 * s] - Ms);
-    o[d] = Elem<T>::from_f(a * inv);
+  const int d4n = head_dim / 4;  // float4 columns; head_dim is a multiple of 8
+  for (int d4b = 0; d4b < d4n; d4b += 32) {  // warp-uniform trip count (shuffles inside)
+    const int d4 = d4b + lane;
+    const bool active = d4 < d4n;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < num_splits; s0 += 32) {
+      // lane j holds the weight of split s0 + j; 0 for empty partials, whose acc was never
+      // written and must not be read (0 * garbage)
+      const int sj = s0 + lane;
+      const float w_mine = (sj < num_splits && ml[2 * sj + 1] > 0.f) ? fast_exp2(ml[2 * sj] - Ms) : 0.f;
+      const int cnt = min(32, num_splits - s0);
+#pragma unroll 4
+      for (int j = 0; j < cnt; j++) {
+        const float w = __shfl_sync(0xffffffffu, w_mine, j);
+        if (w != 0.f && active) {
+          const float4 v = acc[(int64_t)(s0 + j) * d4n + d4];
+          a.x = fmaf(v.x, w, a.x), a.y = fmaf(v.y, w, a.y), a.z = fmaf(v.z, w, a.z), a.w = fmaf(v.w, w, a.w);
+        }
+      }
+    }
+    uint2 packed;
+    packed.x = Elem<T>::from_f2(a.x * inv, a.y * inv);
+    packed.y = Elem<T>::from_f2(a.z * inv, a.w * inv);
+    if (active) *reinterpret_cast<uint2*>(o + d4 * 4) = packed;
   }
   if (lse && lane == 0)
     lse[(b * num_heads + h) * seqlen_q + qi] =

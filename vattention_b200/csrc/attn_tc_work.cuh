@@ -1,0 +1,593 @@
+// Device-side work functions of the tensor-core attention kernels.  One call processes one
+// work item with the whole CTA (256 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 4-7
+// softmax / accumulate):
+//   decode_work   one (chunk of 128-key tiles, kv head, batch entry) of a seqlen_q == 1 problem
+//   prefill_work  one (128-row query block, q head, batch entry) of a seqlen_q > 1 problem
+// The stand-alone decode / prefill kernels call them once; the POD kernel (attn_pod_tc.cu) calls
+// either, item after item, from one persistent CTA per SM.  All mbarriers are (re)initialised at
+// the start of every item, so a work function has no state that outlives it except TMEM/SMEM
+// ownership, which the caller provides.
+//
+// Algorithm notes and the reference lines each function replaces are in attn_decode_tc.cu and
+// attn_prefill_tc.cu.
+#pragma once
+#include "attn_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace vattn {
+namespace tcwork {
+
+using namespace ptx;
+
+constexpr int kThreads = 256;
+constexpr int kTile = 128;     // keys per tile == TMEM lanes
+constexpr int kHeadDim = 128;
+constexpr int kTileBytes = kTile * kHeadDim * 2;  // 32 KB
+
+// position of V_j in the load sequence K0, K1, V0, K2, V1, K3, ... of an n-tile item
+__device__ __forceinline__ int seq_pos_v(int j, int n) {
+  const int c0 = n < 2 ? n : 2;
+  const int extra = n - 2 > 0 ? (j < n - 2 ? j : n - 2) : 0;
+  return c0 + j + extra;
+}
+// byte offset of 16-bit element (row r, col c) inside a [rows x 64] SW128 K-major atom
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1));
+}
+__device__ __forceinline__ void mbar_reinit(uint64_t* bar, uint32_t count, bool was_live) {
+  if (was_live) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  mbar_init(bar, count);
+}
+
+// mbarriers of one CTA; shared by both kinds of work so that a persistent CTA alternating between
+// them re-initialises the same, never-overwritten words
+constexpr int kMaxStages = 6;
+struct TcBarriers {
+  uint64_t full[kMaxStages], empty[kMaxStages];  // TMA ring
+  uint64_t q_full;                               // prefill: Q block landed
+  uint64_t s_full[2], p_ready[2];                // S ready for softmax / P ready for the PV MMA
+  uint64_t o_full[2];                            // decode: O_j^T ready; prefill uses [0] as "PV_j done"
+};
+
+// ======================================================================== decode ====
+constexpr int kNPad = 16;          // MMA N: query heads of the GQA group, zero padded
+constexpr int kDecodeTmemCols = 64;  // S^T x2 (16 columns each) + O^T x2
+
+struct DecodeTcParams {
+  const char* q;
+  char* out;
+  float* lse;
+  float* ws_acc;
+  float* ws_ml;
+  const int32_t* cache_seqlens;
+  const int32_t* cache_batch_idx;
+  int64_t q_b, q_h, o_b, o_h;  // byte strides
+  int seqlen_k, seqlen_new, num_heads, num_kv_heads, group, batch;
+  int tiles_per_chunk, num_chunks;
+  float scale_log2;
+  uint32_t idesc_qk, idesc_pv;
+  uint32_t v_lbo, v_sbo;  // MN-major descriptor strides for the V tile
+};
+
+template <int STAGES>
+struct __align__(1024) DecodeSmemT {
+  uint8_t ring[STAGES][kTileBytes];  // K / V tiles as TMA wrote them (2 x [128 x 128 B] atoms)
+  uint8_t q[2][kNPad * 128];         // Q  : 2 K-atoms of [16 rows x 64 dims], SW128
+  uint8_t p[2][2][kNPad * 128];      // P^T: double buffered, 2 K-atoms of [16 rows x 64 keys]
+  float wmax[2][4][kNPad];           // cross-warp tile max exchange
+  float red[4][kNPad];               // final row-sum exchange
+};
+
+template <typename T, int GP, int STAGES>
+__device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, const DecodeTcParams& p,
+                            DecodeSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem, int chunk, int hkv,
+                            int b, bool barriers_live) {
+  static_assert(STAGES <= kMaxStages, "ring deeper than the barrier block");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = p.cache_batch_idx ? p.cache_batch_idx[b] : b;
+  const int len = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + p.seqlen_new;
+  const int ntiles_seq = (len + kTile - 1) / kTile;
+  const int tile0 = chunk * p.tiles_per_chunk;
+  const int n = min(p.tiles_per_chunk, ntiles_seq - tile0);  // tiles of this item
+  const int G = p.group;
+  const int h0 = hkv * G;
+
+  if (n <= 0) {
+    // nothing to do for this chunk: publish an empty partial so the combine skips it
+    if (p.num_chunks > 1) {
+      if (threadIdx.x < G) {
+        const int64_t base = ((int64_t)b * p.num_heads + h0 + threadIdx.x) * p.num_chunks + chunk;
+        p.ws_ml[base * 2] = -INFINITY;
+        p.ws_ml[base * 2 + 1] = 0.f;
+      }
+    } else {
+      // zero-length sequence: output zeros (softmax.h:76-78 convention)
+      for (int i = threadIdx.x; i < G * kHeadDim; i += kThreads)
+        reinterpret_cast<T*>(p.out + b * p.o_b + (int64_t)(h0 + i / kHeadDim) * p.o_h)[i % kHeadDim] =
+            Elem<T>::from_f(0.f);
+      if (p.lse && threadIdx.x < G) p.lse[(int64_t)b * p.num_heads + h0 + threadIdx.x] = INFINITY;
+    }
+    return;  // CTA-uniform
+  }
+
+  // ---------------------------------------------------------------- setup ----
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_reinit(&bar.full[s], 1, barriers_live);
+      mbar_reinit(&bar.empty[s], 1, barriers_live);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_reinit(&bar.s_full[i], 1, barriers_live);
+      mbar_reinit(&bar.p_ready[i], 128, barriers_live);
+      mbar_reinit(&bar.o_full[i], 1, barriers_live);
+    }
+    fence_mbar_init();
+  }
+  {
+    // zero Q and P^T (rows >= G must stay zero), then stage this group's query heads
+    uint32_t* z = reinterpret_cast<uint32_t*>(sm.q);
+    for (int i = threadIdx.x; i < (int)(sizeof(sm.q) + sizeof(sm.p)) / 4; i += kThreads) z[i] = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * (kHeadDim / 8); i += kThreads) {
+    const int g = i / (kHeadDim / 8), c8 = i % (kHeadDim / 8);  // 16-byte chunk c8 of head g
+    const uint4 v = *reinterpret_cast<const uint4*>(p.q + b * p.q_b + (int64_t)(h0 + g) * p.q_h + c8 * 16);
+    *reinterpret_cast<uint4*>(sm.q[c8 >> 3] + sw128_off(g, (c8 & 7) * 8)) = v;
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  if (warp == 0) {
+    // =========================================================== TMA producer ====
+    if (lane == 0) {
+      int pos = 0;
+      auto load = [&](const CUtensorMap* m, int tile) {
+        const int s = pos % STAGES;
+        mbar_wait(&bar.empty[s], ((pos / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&bar.full[s], kTileBytes);
+        tma_load_5d(sm.ring[s], m, &bar.full[s], 0, (tile0 + tile) * kTile, 0, hkv, slot);
+        pos++;
+      };
+      load(kmap, 0);
+      if (n > 1) load(kmap, 1);
+      for (int j = 0; j < n; j++) {
+        load(vmap, j);
+        if (j + 2 < n) load(kmap, j + 2);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer ====
+    if (lane == 0) {
+      int pos = 0;
+      const uint32_t q_addr = smem_u32(sm.q[0]);
+      auto issue_qk = [&](int j) {
+        const int s = pos % STAGES;
+        mbar_wait(&bar.full[s], (pos / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sm.ring[s]);
+#pragma unroll
+        for (int ks = 0; ks < kHeadDim / 16; ks++) {
+          const uint32_t a = a0 + (ks >> 2) * (kTile * 128) + (ks & 3) * 32;
+          const uint32_t bq = q_addr + (ks >> 2) * (kNPad * 128) + (ks & 3) * 32;
+          umma_ss(tmem + (j & 1) * kNPad, make_smem_desc(a, 16, 1024, kLayoutSw128),
+                  make_smem_desc(bq, 16, 1024, kLayoutSw128), p.idesc_qk, ks > 0);
+        }
+        umma_commit(&bar.empty[s]);       // K tile consumed
+        umma_commit(&bar.s_full[j & 1]);  // S^T_j ready for the softmax warps
+        pos++;
+      };
+      auto issue_pv = [&](int j) {
+        const int s = pos % STAGES;
+        mbar_wait(&bar.full[s], (pos / STAGES) & 1);
+        mbar_wait(&bar.p_ready[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sm.ring[s]);
+        const uint32_t p_addr = smem_u32(sm.p[j & 1][0]);
+#pragma unroll
+        for (int ks = 0; ks < kTile / 16; ks++) {
+          const uint32_t a = a0 + ks * (16 * 128);  // 16 keys further down the tile
+          const uint32_t bp = p_addr + (ks >> 2) * (kNPad * 128) + (ks & 3) * 32;
+          umma_ss(tmem + 2 * kNPad + (j & 1) * kNPad, make_smem_desc(a, p.v_lbo, p.v_sbo, kLayoutSw128),
+                  make_smem_desc(bp, 16, 1024, kLayoutSw128), p.idesc_pv, ks > 0);
+        }
+        umma_commit(&bar.empty[s]);       // V tile consumed
+        umma_commit(&bar.o_full[j & 1]);  // O_j^T ready
+        pos++;
+      };
+      issue_qk(0);
+      if (n > 1) issue_qk(1);
+      for (int j = 0; j < n; j++) {
+        issue_pv(j);
+        if (j + 2 < n) issue_qk(j + 2);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================= softmax / accumulate ====
+    const int t = threadIdx.x - 128;  // key index inside a tile for S^T, head dim for O^T
+    const int sw = warp - 4;          // TMEM lane quadrant of this warp
+    const uint32_t lane_base = (uint32_t)(sw * 32) << 16;
+    float m_run[GP], l_thr[GP], acc[GP], alpha_prev[GP];
+#pragma unroll
+    for (int g = 0; g < GP; g++) {
+      m_run[g] = -INFINITY;
+      l_thr[g] = 0.f;
+      acc[g] = 0.f;
+      alpha_prev[g] = 1.f;
+    }
+    auto load_cols = [&](uint32_t col, float (&dst)[GP]) {
+      uint32_t r[GP];
+      if constexpr (GP == 4) tmem_ld_x4(tmem + lane_base + col, r);
+      else if constexpr (GP == 8) tmem_ld_x8(tmem + lane_base + col, r);
+      else tmem_ld_x16(tmem + lane_base + col, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < GP; g++) dst[g] = __uint_as_float(r[g]);
+    };
+    auto accumulate_o = [&](int j) {  // acc = acc * alpha_j + O_j^T
+      mbar_wait(&bar.o_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float o[GP];
+      load_cols(2 * kNPad + (j & 1) * kNPad, o);
+#pragma unroll
+      for (int g = 0; g < GP; g++) acc[g] = fmaf(acc[g], alpha_prev[g], o[g]);
+    };
+
+    for (int j = 0; j < n; j++) {
+      mbar_wait(&bar.s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float s[GP];
+      load_cols((j & 1) * kNPad, s);
+      const int key = (tile0 + j) * kTile + t;
+      const bool valid = key < len;
+      float mx[GP];
+#pragma unroll
+      for (int g = 0; g < GP; g++) {
+        s[g] = valid ? s[g] * p.scale_log2 : -INFINITY;
+        mx[g] = s[g];
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+        for (int g = 0; g < GP; g++) mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], off));
+      // every lane holds every head's warp max after the butterfly; lane g publishes head g
+#pragma unroll
+      for (int g = 0; g < GP; g++)
+        if (lane == g) sm.wmax[j & 1][sw][g] = mx[g];
+      named_bar_sync(1, 128);
+      // the previous tile's O^T can be folded in while this tile's P is being produced
+      if (j > 0) accumulate_o(j - 1);
+      const bool tail = (tile0 + j + 1) * kTile > len;  // last, partial tile of the sequence
+      uint8_t* pbuf = sm.p[j & 1][t >> 6];
+#pragma unroll
+      for (int g = 0; g < GP; g++) {
+        const float tm = fmaxf(fmaxf(sm.wmax[j & 1][0][g], sm.wmax[j & 1][1][g]),
+                               fmaxf(sm.wmax[j & 1][2][g], sm.wmax[j & 1][3][g]));
+        const float m_new = fmaxf(m_run[g], tm);  // finite: every tile holds >= 1 valid key
+        const float alpha = fast_exp2(m_run[g] - m_new);
+        const float pr = fast_exp2(s[g] - m_new);
+        m_run[g] = m_new;
+        alpha_prev[g] = alpha;
+        l_thr[g] = fmaf(l_thr[g], alpha, pr);
+        if (g < G) *reinterpret_cast<T*>(pbuf + sw128_off(g, t & 63)) = Elem<T>::from_f(pr);
+      }
+      if (tail) {
+        // rows past the sequence end hold whatever was in memory; P is 0 there, but 0 * NaN
+        // would poison O, so blank those V rows in shared memory before the MMA reads them
+        const int pv = seq_pos_v(j, n);
+        mbar_wait(&bar.full[pv % STAGES], (pv / STAGES) & 1);
+        if (!valid) {
+          uint8_t* vt = sm.ring[pv % STAGES];
+#pragma unroll
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+              *reinterpret_cast<uint4*>(vt + a * (kTile * 128) + t * 128 + c * 16) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bar.p_ready[j & 1]);
+    }
+    accumulate_o(n - 1);
+
+    // ---- epilogue: row sums across the 128 key-threads, then publish ----
+    float lsum[GP];
+#pragma unroll
+    for (int g = 0; g < GP; g++) lsum[g] = l_thr[g];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+      for (int g = 0; g < GP; g++) lsum[g] += __shfl_xor_sync(0xffffffffu, lsum[g], off);
+#pragma unroll
+    for (int g = 0; g < GP; g++)
+      if (lane == g) sm.red[sw][g] = lsum[g];
+    named_bar_sync(1, 128);
+#pragma unroll
+    for (int g = 0; g < GP; g++) {
+      if (g >= G) continue;
+      const float L = sm.red[0][g] + sm.red[1][g] + sm.red[2][g] + sm.red[3][g];
+      const int h = h0 + g;
+      if (p.num_chunks == 1) {
+        const float inv = L > 0.f ? 1.f / L : 0.f;
+        reinterpret_cast<T*>(p.out + b * p.o_b + (int64_t)h * p.o_h)[t] = Elem<T>::from_f(acc[g] * inv);
+        if (p.lse && t == 0)
+          p.lse[(int64_t)b * p.num_heads + h] = L > 0.f ? (m_run[g] + log2f(L)) * 0.6931471805599453f : INFINITY;
+      } else {
+        const int64_t base = ((int64_t)b * p.num_heads + h) * p.num_chunks + chunk;
+        p.ws_acc[base * kHeadDim + t] = acc[g];
+        if (t == 0) {
+          p.ws_ml[base * 2] = m_run[g];
+          p.ws_ml[base * 2 + 1] = L;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+}
+
+// ======================================================================= prefill ====
+constexpr int kPrefillStages = 5;
+constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;  // TMEM columns: S x2 | O | P x2 (packed)
+constexpr float kRescaleThreshold = 8.f;                // log2 domain
+
+struct PrefillParams {
+  char* out;
+  float* lse;
+  const int32_t* cache_seqlens;
+  const int32_t* cache_batch_idx;
+  int64_t o_b, o_r, o_h;  // byte strides
+  int seqlen_q, seqlen_k, seqlen_new, num_heads, group, num_m_tiles, batch;
+  int causal;
+  float scale_log2;
+  uint32_t idesc_qk, idesc_pv;
+  uint32_t v_lbo, v_sbo;
+};
+
+struct __align__(1024) PrefillSmem {
+  uint8_t q[kTile * kHeadDim * 2];
+  uint8_t ring[kPrefillStages][kTileBytes];
+};
+
+template <typename T>
+__device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
+                             const PrefillParams& p, PrefillSmem& sm, TcBarriers& bar, uint32_t tmem, int mt,
+                             int h, int b, bool barriers_live) {
+  constexpr int kStages = kPrefillStages;
+  constexpr int kBM = kTile, kBN = kTile, kD = kHeadDim;
+  const int hkv = h / p.group;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = p.cache_batch_idx ? p.cache_batch_idx[b] : b;
+  const int lk = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + p.seqlen_new;
+  const int m0 = mt * kBM;
+  const int rows = min(kBM, p.seqlen_q - m0);
+  // key j is visible to query row i iff j < lk and (not causal or j <= i + lk - seqlen_q)  (mask.h:172)
+  const int shift = lk - p.seqlen_q;
+  int kv_end = lk;
+  if (p.causal) kv_end = min(lk, m0 + rows + shift);  // exclusive bound for the block's last row
+  if (kv_end < 0) kv_end = 0;
+  const int n = (kv_end + kBN - 1) / kBN;
+
+  if (threadIdx.x == 0) {
+    mbar_reinit(&bar.q_full, 1, barriers_live);
+    for (int s = 0; s < kStages; s++) {
+      mbar_reinit(&bar.full[s], 1, barriers_live);
+      mbar_reinit(&bar.empty[s], 1, barriers_live);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_reinit(&bar.s_full[i], 1, barriers_live);
+      mbar_reinit(&bar.p_ready[i], 128, barriers_live);
+      mbar_reinit(&bar.o_full[i], 1, barriers_live);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // =========================================================== TMA producer ====
+    if (lane == 0 && n > 0) {
+      mbar_expect_tx(&bar.q_full, kBM * kD * 2);
+      tma_load_5d(sm.q, qmap, &bar.q_full, 0, m0, 0, h, b);
+      int pos = 0;
+      auto load = [&](const CUtensorMap* m, int tile) {
+        const int s = pos % kStages;
+        mbar_wait(&bar.empty[s], ((pos / kStages) & 1) ^ 1);
+        mbar_expect_tx(&bar.full[s], kTileBytes);
+        tma_load_5d(sm.ring[s], m, &bar.full[s], 0, tile * kBN, 0, hkv, slot);
+        pos++;
+      };
+      load(kmap, 0);
+      if (n > 1) load(kmap, 1);
+      for (int j = 0; j < n; j++) {
+        load(vmap, j);
+        if (j + 2 < n) load(kmap, j + 2);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer ====
+    if (lane == 0 && n > 0) {
+      int pos = 0;
+      const uint32_t q_addr = smem_u32(sm.q);
+      mbar_wait(&bar.q_full, 0);
+      auto issue_qk = [&](int j) {
+        const int s = pos % kStages;
+        mbar_wait(&bar.full[s], (pos / kStages) & 1);
+        tc_fence_after();
+        const uint32_t k0 = smem_u32(sm.ring[s]);
+#pragma unroll
+        for (int ks = 0; ks < kD / 16; ks++) {
+          const uint32_t off = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
+          umma_ss(tmem + kColS + (j & 1) * kBN, make_smem_desc(q_addr + off, 16, 1024, kLayoutSw128),
+                  make_smem_desc(k0 + off, 16, 1024, kLayoutSw128), p.idesc_qk, ks > 0);
+        }
+        umma_commit(&bar.empty[s]);
+        umma_commit(&bar.s_full[j & 1]);
+        pos++;
+      };
+      auto issue_pv = [&](int j) {
+        const int s = pos % kStages;
+        mbar_wait(&bar.full[s], (pos / kStages) & 1);
+        mbar_wait(&bar.p_ready[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t v0 = smem_u32(sm.ring[s]);
+#pragma unroll
+        for (int ks = 0; ks < kBN / 16; ks++) {
+          // A: 16 keys = 8 packed TMEM columns of P_j; B: 16 key rows further down the V tile
+          umma_ts(tmem + kColO, tmem + kColP + (j & 1) * (kBN / 2) + ks * 8,
+                  make_smem_desc(v0 + ks * (16 * 128), p.v_lbo, p.v_sbo, kLayoutSw128), p.idesc_pv,
+                  (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&bar.empty[s]);
+        umma_commit(&bar.o_full[0]);  // completes phase j
+        pos++;
+      };
+      issue_qk(0);
+      if (n > 1) issue_qk(1);
+      for (int j = 0; j < n; j++) {
+        issue_pv(j);
+        if (j + 2 < n) issue_qk(j + 2);
+      }
+    }
+  } else if (warp >= 4) {
+    // ==================================================== softmax / epilogue ====
+    const int i = threadIdx.x - 128;  // query row inside the block == TMEM lane
+    const int sw = warp - 4;
+    const uint32_t lane_base = (uint32_t)(sw * 32) << 16;
+    const int qi = m0 + i;
+    // last visible key (inclusive) for this row; < 0 means the row sees nothing
+    int limit = lk - 1;
+    if (p.causal) limit = min(limit, qi + shift);
+    float m_ref = -INFINITY;  // reference max the stored exponentials are relative to
+    float l = 0.f;
+
+    for (int j = 0; j < n; j++) {
+      mbar_wait(&bar.s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem + lane_base + kColS + (j & 1) * kBN;
+      const int key0 = j * kBN;
+      const bool need_mask = key0 + kBN - 1 > limit;  // per-thread; false for interior tiles
+      // pass 1: row max of the tile
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kBN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(s_addr + c, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          float v = __uint_as_float(r[e]);
+          if (need_mask && key0 + c + e > limit) v = -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      mx *= p.scale_log2;  // scale > 0: max commutes with the scaling
+      // lazy rescale: advance the reference only if this row outgrew it by > 2^8
+      float alpha = 1.f;
+      bool grow = mx > m_ref + kRescaleThreshold;
+      if (m_ref == -INFINITY && mx > -INFINITY) grow = true;  // first visible key of the row
+      if (grow) {
+        alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - mx);
+        m_ref = mx;
+      }
+      const bool any_grow = __any_sync(0xffffffffu, grow) && j > 0;
+      if (any_grow) {
+        // O holds sum_{t<j} P_t V_t relative to the old reference: wait for PV_{j-1}, then scale
+        mbar_wait(&bar.o_full[0], (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < kD; c += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(tmem + lane_base + kColO + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+          tmem_st_x32(tmem + lane_base + kColO + c, r);
+        }
+        tmem_wait_st();
+      }
+      l *= alpha;
+      // pass 2: exponentials, row sum, pack to 16 bit, store P_j to TMEM
+      const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
+      const uint32_t p_addr = tmem + lane_base + kColP + (j & 1) * (kBN / 2);
+#pragma unroll
+      for (int c = 0; c < kBN; c += 64) {
+        uint32_t packed[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          uint32_t r[32];
+          tmem_ld_x32(s_addr + c + hh * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float v0 = __uint_as_float(r[e]), v1 = __uint_as_float(r[e + 1]);
+            float p0 = fast_exp2(fmaf(v0, p.scale_log2, -mref_safe));
+            float p1 = fast_exp2(fmaf(v1, p.scale_log2, -mref_safe));
+            if (need_mask) {
+              if (key0 + c + hh * 32 + e > limit) p0 = 0.f;
+              if (key0 + c + hh * 32 + e + 1 > limit) p1 = 0.f;
+            }
+            l += p0 + p1;
+            packed[hh * 16 + e / 2] = Elem<T>::from_f2(p0, p1);
+          }
+        }
+        tmem_st_x32(p_addr + c / 2, packed);
+      }
+      tmem_wait_st();
+      if ((j + 1) * kBN > lk) {
+        // tail tile: key rows past the sequence end are uninitialised memory; P is 0 there but
+        // 0 * NaN would poison O, so blank those V rows in shared memory first
+        const int pv = seq_pos_v(j, n);
+        mbar_wait(&bar.full[pv % kStages], (pv / kStages) & 1);
+        if (key0 + i >= lk) {
+          uint8_t* vt = sm.ring[pv % kStages];
+#pragma unroll
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+              *reinterpret_cast<uint4*>(vt + a * (kBN * 128) + i * 128 + c * 16) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      mbar_arrive(&bar.p_ready[j & 1]);
+    }
+
+    // ---- epilogue: O / l -> 16 bit -> global ----
+    if (n > 0) {
+      mbar_wait(&bar.o_full[0], (n - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    char* orow = p.out + b * p.o_b + (int64_t)qi * p.o_r + (int64_t)h * p.o_h;
+#pragma unroll
+    for (int c = 0; c < kD; c += 32) {
+      uint32_t r[32];
+      if (n > 0) {
+        tmem_ld_x32(tmem + lane_base + kColO + c, r);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e++) r[e] = 0;
+      }
+      if (i < rows) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          o.x = Elem<T>::from_f2(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+          o.y = Elem<T>::from_f2(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
+          o.z = Elem<T>::from_f2(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
+          o.w = Elem<T>::from_f2(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + (c + e) * 2) = o;
+        }
+      }
+    }
+    if (p.lse && i < rows)
+      p.lse[((int64_t)b * p.num_heads + h) * p.seqlen_q + qi] =
+          l > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+}
+
+}  // namespace tcwork
+}  // namespace vattn

@@ -32,6 +32,10 @@ bool prefill_tc_supported(const vattn_fwd_params_t&, std::string* why);
 size_t prefill_tc_workspace(const vattn_fwd_params_t&);
 void launch_prefill_tc(const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
 int run_umma_selftest(char* buf, size_t len, cudaStream_t);
+// fused prefill + decode (attn_pod_tc.cu)
+bool pod_tc_supported(const vattn_fwd_params_t&, const vattn_fwd_params_t&, std::string* why);
+size_t pod_tc_workspace(const vattn_fwd_params_t&, const vattn_fwd_params_t&);
+void launch_pod_tc(const vattn_fwd_params_t&, const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
 
 // ---- per-launch kernel timing -------------------------------------------------------
 namespace {
@@ -233,7 +237,23 @@ int vattn_single_prefill(const void* q, int64_t q_row_stride, int64_t q_head_str
   return vattn_fwd_kvcache(&p, stream);
 }
 
+static bool pod_fused_path(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode) {
+  if (!prefill || !decode) return false;
+  if (prefill->impl == VATTN_IMPL_SIMT || decode->impl == VATTN_IMPL_SIMT) return false;
+  if (prefill->batch == 0 || decode->batch == 0) return false;
+  std::string why;
+  return pod_tc_supported(*prefill, *decode, &why);
+}
+
 size_t vattn_pod_workspace(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode) {
+  try {
+    if (prefill) validate(*prefill);
+    if (decode) validate(*decode);
+    if (pod_fused_path(prefill, decode)) return pod_tc_workspace(*prefill, *decode);
+  } catch (...) {
+    translate_attn_exception();
+    return 0;
+  }
   size_t a = prefill ? vattn_fwd_kvcache_workspace(prefill) : 0;
   size_t b = decode ? vattn_fwd_kvcache_workspace(decode) : 0;
   a = (a + 255) / 256 * 256;
@@ -242,8 +262,17 @@ size_t vattn_pod_workspace(const vattn_fwd_params_t* prefill, const vattn_fwd_pa
 
 int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode,
                   int32_t fused_params, void* workspace, size_t workspace_bytes, void* stream) {
+  // fused_params selects tile shapes / the HFuse baseline in the reference (fused_api.cpp:24-53);
+  // there is one schedule here, the value is accepted for signature compatibility
   (void)fused_params;
   try {
+    if (prefill) validate(*prefill);
+    if (decode) validate(*decode);
+    if (pod_fused_path(prefill, decode)) {
+      launch_pod_tc(*prefill, *decode, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+      return VATTN_OK;
+    }
+    // one side missing, or a shape the tensor-core path does not take: the two calls back to back
     size_t a = prefill ? vattn_fwd_kvcache_workspace(prefill) : 0;
     a = (a + 255) / 256 * 256;
     if (prefill) {
