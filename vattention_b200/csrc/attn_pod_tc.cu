@@ -94,12 +94,13 @@ pod_tc_kernel(const __grid_constant__ CUtensorMap qmap_p, const __grid_constant_
     if (t >= total) break;
     const long long np0 = t * sch.n_prefill / total, np1 = (t + 1) * sch.n_prefill / total;
     if (np1 > np0) {
-      // prefill item np0: row blocks heavy-first, then heads, then batch
-      const long long per_mt = (long long)pp.num_heads * pp.batch;
-      const int mt = pp.num_m_tiles - 1 - (int)(np0 / per_mt);
-      const int rem = (int)(np0 % per_mt);
-      prefill_work<T>(&qmap_p, &kmap_p, &vmap_p, pp, sm.u.prefill, sm.bar, tmem, mt, rem % pp.num_heads,
-                      rem / pp.num_heads, true);
+      // prefill item np0, in the stand-alone kernel's launch order: row blocks of one (batch, head)
+      // are consecutive (heavy first), so the CTAs running at the same time share that head's
+      // K/V in L2 instead of streaming 148 different heads through it
+      const int mt = pp.num_m_tiles - 1 - (int)(np0 % pp.num_m_tiles);
+      const long long rem = np0 / pp.num_m_tiles;
+      prefill_work<T>(&qmap_p, &kmap_p, &vmap_p, pp, sm.u.prefill, sm.bar, tmem, mt,
+                      (int)(rem % pp.num_heads), (int)(rem / pp.num_heads), true);
     } else {
       const long long d = t - np0;  // decode item: chunk fastest, then kv head, then batch
       const int chunk = (int)(d % dp.num_chunks);

@@ -349,6 +349,71 @@ struct __align__(1024) PrefillSmem {
   uint8_t ring[kPrefillStages][kTileBytes];
 };
 
+// Row max of one S tile (thread = query row).  MASK is a warp-uniform choice: interior tiles
+// (the vast majority) pay no per-element compare.  Four independent max chains: with one softmax
+// warp per scheduler there is nothing else to hide the 4-cycle dependent-issue latency.
+template <bool MASK>
+__device__ __forceinline__ float tile_row_max(uint32_t s_addr, int key0, int limit) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < kTile; c += 32) {
+    uint32_t r[32];
+    tmem_ld_x32(s_addr + c, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      float v0 = __uint_as_float(r[e]), v1 = __uint_as_float(r[e + 1]);
+      float v2 = __uint_as_float(r[e + 2]), v3 = __uint_as_float(r[e + 3]);
+      if (MASK) {
+        const int k = key0 + c + e;
+        if (k > limit) v0 = -INFINITY;
+        if (k + 1 > limit) v1 = -INFINITY;
+        if (k + 2 > limit) v2 = -INFINITY;
+        if (k + 3 > limit) v3 = -INFINITY;
+      }
+      m0 = fmaxf(m0, v0), m1 = fmaxf(m1, v1), m2 = fmaxf(m2, v2), m3 = fmaxf(m3, v3);
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// p = exp2(s * scale - mref) for one S tile, packed to 16 bit and stored to TMEM as the A operand of
+// the PV MMA (2 keys per 32-bit column); returns the row sum of the (unrounded) exponentials.
+template <typename T, bool MASK>
+__device__ __forceinline__ float tile_exp_store(uint32_t s_addr, uint32_t p_addr, float scale_log2,
+                                                float mref, int key0, int limit) {
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+  for (int c = 0; c < kTile; c += 64) {
+    uint32_t packed[32];
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      uint32_t r[32];
+      tmem_ld_x32(s_addr + c + hh * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        float p0 = fast_exp2(fmaf(__uint_as_float(r[e]), scale_log2, -mref));
+        float p1 = fast_exp2(fmaf(__uint_as_float(r[e + 1]), scale_log2, -mref));
+        float p2 = fast_exp2(fmaf(__uint_as_float(r[e + 2]), scale_log2, -mref));
+        float p3 = fast_exp2(fmaf(__uint_as_float(r[e + 3]), scale_log2, -mref));
+        if (MASK) {
+          const int k = key0 + c + hh * 32 + e;
+          if (k > limit) p0 = 0.f;
+          if (k + 1 > limit) p1 = 0.f;
+          if (k + 2 > limit) p2 = 0.f;
+          if (k + 3 > limit) p3 = 0.f;
+        }
+        l0 += p0, l1 += p1, l2 += p2, l3 += p3;
+        packed[hh * 16 + e / 2] = Elem<T>::from_f2(p0, p1);
+        packed[hh * 16 + e / 2 + 1] = Elem<T>::from_f2(p2, p3);
+      }
+    }
+    tmem_st_x32(p_addr + c / 2, packed);
+  }
+  return (l0 + l1) + (l2 + l3);
+}
+
 template <typename T>
 __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
                              const PrefillParams& p, PrefillSmem& sm, TcBarriers& bar, uint32_t tmem, int mt,
@@ -466,20 +531,10 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
       const uint32_t s_addr = tmem + lane_base + kColS + (j & 1) * kBN;
       const int key0 = j * kBN;
       const bool need_mask = key0 + kBN - 1 > limit;  // per-thread; false for interior tiles
+      // masking is decided per warp so that interior tiles run the compare-free variant
+      const bool warp_mask = __any_sync(0xffffffffu, need_mask);
       // pass 1: row max of the tile
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < kBN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(s_addr + c, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 32; e++) {
-          float v = __uint_as_float(r[e]);
-          if (need_mask && key0 + c + e > limit) v = -INFINITY;
-          mx = fmaxf(mx, v);
-        }
-      }
+      float mx = warp_mask ? tile_row_max<true>(s_addr, key0, limit) : tile_row_max<false>(s_addr, key0, limit);
       mx *= p.scale_log2;  // scale > 0: max commutes with the scaling
       // lazy rescale: advance the reference only if this row outgrew it by > 2^8
       float alpha = 1.f;
@@ -509,29 +564,8 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
       // pass 2: exponentials, row sum, pack to 16 bit, store P_j to TMEM
       const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
       const uint32_t p_addr = tmem + lane_base + kColP + (j & 1) * (kBN / 2);
-#pragma unroll
-      for (int c = 0; c < kBN; c += 64) {
-        uint32_t packed[32];
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          uint32_t r[32];
-          tmem_ld_x32(s_addr + c + hh * 32, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float v0 = __uint_as_float(r[e]), v1 = __uint_as_float(r[e + 1]);
-            float p0 = fast_exp2(fmaf(v0, p.scale_log2, -mref_safe));
-            float p1 = fast_exp2(fmaf(v1, p.scale_log2, -mref_safe));
-            if (need_mask) {
-              if (key0 + c + hh * 32 + e > limit) p0 = 0.f;
-              if (key0 + c + hh * 32 + e + 1 > limit) p1 = 0.f;
-            }
-            l += p0 + p1;
-            packed[hh * 16 + e / 2] = Elem<T>::from_f2(p0, p1);
-          }
-        }
-        tmem_st_x32(p_addr + c / 2, packed);
-      }
+      l += warp_mask ? tile_exp_store<T, true>(s_addr, p_addr, p.scale_log2, mref_safe, key0, limit)
+                     : tile_exp_store<T, false>(s_addr, p_addr, p.scale_log2, mref_safe, key0, limit);
       tmem_wait_st();
       if ((j + 1) * kBN > lk) {
         // tail tile: key rows past the sequence end are uninitialised memory; P is 0 there but
@@ -554,6 +588,10 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
 
     // ---- epilogue: O / l -> 16 bit -> global ----
     if (n > 0) {
+      // S_{n-1} being ready only proves PV_{n-3} retired, so the barrier may still be in phase
+      // n-2: a parity wait for phase n-1 alone would be satisfied by the stale phase n-3 (same
+      // parity).  Wait for the two outstanding phases in order.
+      if (n > 1) mbar_wait(&bar.o_full[0], (n - 2) & 1);
       mbar_wait(&bar.o_full[0], (n - 1) & 1);
       tc_fence_after();
     }
