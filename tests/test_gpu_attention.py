@@ -108,12 +108,16 @@ def test_decode_split_counts(dtype, impl, splits):
     (1, 200, 8, 8, 64, 200, False),    # head_dim 64
     (2, 16, 8, 2, 128, 256, True),     # multi-token append + causal
     (1, 256, 32, 4, 128, 1024, False), # Yi-6B heads
+    (2, 300, 8, 2, 128, 1500, False),  # two row blocks per CTA, second one partial, ragged lengths
+    (1, 513, 8, 2, 128, 513, False),   # odd number of row blocks, square causal
+    (1, 384, 4, 4, 128, 2048, False),  # chunk deep inside a long context
+    (1, 640, 8, 8, 128, 200, False),   # seqlen_q > seqlen_k: leading rows see nothing
 ])
 def test_prefill_matches_oracle(dtype, impl, B, Sq, Hq, Hkv, D, Sk, new):
     case = make_case(B, Sq, Hq, Hkv, D, Sk, dtype, seed=Sq, ragged=B > 1, new=new)
     q, kc, vc, kn, vn, lens, idx = case
     if not new:  # cache_seqlens is the TOTAL length incl. this chunk (wrapper.py:145-166)
-        lens = torch.clamp(lens, min=Sq)
+        lens = torch.clamp(lens, min=min(Sq, Sk))
         case = (q, kc, vc, kn, vn, lens, idx)
     out, want, _ = run_both(case, causal=True, impl=impl)
     close(out, want, dtype)

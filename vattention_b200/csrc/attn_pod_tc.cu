@@ -35,7 +35,8 @@ constexpr int kPodDecodeStages = 6;
 
 struct __align__(1024) PodSmem {
   union {
-    PrefillSmem prefill;
+    PrefillSmem prefill;     // chunks of <= 128 rows: one row block per item
+    Prefill2Smem prefill2;   // otherwise two row blocks per item (ping-pong softmax warpgroups)
     DecodeSmemT<kPodDecodeStages> decode;
   } u;
   TcBarriers bar;
@@ -46,10 +47,12 @@ struct __align__(1024) PodSmem {
 struct PodSched {
   int* counter;       // zeroed before launch
   long long n_prefill, n_decode;
+  int prefill_blocks;  // row blocks per prefill item (1 or 2)
+  int prefill_items_per_head;
 };
 
 template <typename T, int GP>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kPrefill2Threads, 1)
 pod_tc_kernel(const __grid_constant__ CUtensorMap qmap_p, const __grid_constant__ CUtensorMap kmap_p,
               const __grid_constant__ CUtensorMap vmap_p, const __grid_constant__ CUtensorMap kmap_d,
               const __grid_constant__ CUtensorMap vmap_d, const PrefillParams pp, const DecodeTcParams dp,
@@ -97,10 +100,13 @@ pod_tc_kernel(const __grid_constant__ CUtensorMap qmap_p, const __grid_constant_
       // prefill item np0, in the stand-alone kernel's launch order: row blocks of one (batch, head)
       // are consecutive (heavy first), so the CTAs running at the same time share that head's
       // K/V in L2 instead of streaming 148 different heads through it
-      const int mt = pp.num_m_tiles - 1 - (int)(np0 % pp.num_m_tiles);
-      const long long rem = np0 / pp.num_m_tiles;
-      prefill_work<T>(&qmap_p, &kmap_p, &vmap_p, pp, sm.u.prefill, sm.bar, tmem, mt,
-                      (int)(rem % pp.num_heads), (int)(rem / pp.num_heads), true);
+      const int mi = sch.prefill_items_per_head - 1 - (int)(np0 % sch.prefill_items_per_head);
+      const long long rem = np0 / sch.prefill_items_per_head;
+      const int h = (int)(rem % pp.num_heads), b = (int)(rem / pp.num_heads);
+      if (sch.prefill_blocks == 2)
+        prefill2_work<T>(&qmap_p, &kmap_p, &vmap_p, pp, sm.u.prefill2, sm.bar, tmem, mi, h, b, true);
+      else
+        prefill_work<T>(&qmap_p, &kmap_p, &vmap_p, pp, sm.u.prefill, sm.bar, tmem, mi, h, b, true);
     } else {
       const long long d = t - np0;  // decode item: chunk fastest, then kv head, then batch
       const int chunk = (int)(d % dp.num_chunks);
@@ -124,7 +130,9 @@ void launch_pod_t(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, 
   build_decode_tc(dec, dec_ws, &Dl);
   PodSched sch;
   sch.counter = counter;
-  sch.n_prefill = (long long)P.pp.num_m_tiles * pre.num_heads * pre.batch;
+  sch.prefill_blocks = pre.seqlen_q > kTile ? 2 : 1;
+  sch.prefill_items_per_head = (P.pp.num_m_tiles + sch.prefill_blocks - 1) / sch.prefill_blocks;
+  sch.n_prefill = (long long)sch.prefill_items_per_head * pre.num_heads * pre.batch;
   sch.n_decode = (long long)Dl.dp.num_chunks * dec.num_kv_heads * dec.batch;
   VATTN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
   launch_append_kv(dec, stream);
@@ -138,7 +146,7 @@ void launch_pod_t(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, 
   auto launch = [&](auto kernel) {
     VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tslot = timing_begin(stream);
-    kernel<<<grid, kThreads, smem, stream>>>(P.qmap, P.kmap, P.vmap, Dl.kmap, Dl.vmap, P.pp, Dl.dp, sch);
+    kernel<<<grid, kPrefill2Threads, smem, stream>>>(P.qmap, P.kmap, P.vmap, Dl.kmap, Dl.vmap, P.pp, Dl.dp, sch);
     timing_end(tslot, stream);
   };
   if (group <= 4) launch(pod_tc_kernel<T, 4>);

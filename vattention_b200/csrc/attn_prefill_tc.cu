@@ -67,6 +67,41 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constan
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+struct __align__(1024) Prefill2KernelSmem {
+  Prefill2Smem data;
+  TcBarriers bar;
+  uint32_t tmem_base;
+};
+
+// two 128-row blocks per CTA with one softmax warpgroup each (prefill2_work)
+template <typename T>
+__global__ void __launch_bounds__(kPrefill2Threads, 1)
+prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                   const __grid_constant__ CUtensorMap vmap, const PrefillParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  Prefill2KernelSmem& sm =
+      *reinterpret_cast<Prefill2KernelSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0 && (threadIdx.x & 31) == 0) {
+    prefetch_tensormap(&qmap);
+    prefetch_tensormap(&kmap);
+    prefetch_tensormap(&vmap);
+  }
+  if (warp == 2) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const int pairs = (p.num_m_tiles + 1) / 2;
+  prefill2_work<T>(&qmap, &kmap, &vmap, p, sm.data, sm.bar, tmem, pairs - 1 - blockIdx.x, blockIdx.y,
+                   blockIdx.z, false);
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
 int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return v ? std::atoi(v) : dflt;
@@ -76,11 +111,21 @@ template <typename T>
 void launch_t(const vattn_fwd_params_t& p, cudaStream_t stream) {
   PrefillTcLaunch L;
   build_prefill_tc(p, &L);
-  const size_t smem = sizeof(PrefillKernelSmem) + 1024;
-  VATTN_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(L.pp.num_m_tiles, p.num_heads, p.batch);
   const int tslot = timing_begin(stream);
-  prefill_tc_kernel<T><<<grid, kThreads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.pp);
+  // two row blocks per CTA need enough (pair, head, batch) items to fill the SMs; short chunks
+  // keep one block per CTA
+  const long long pair_items = (long long)((L.pp.num_m_tiles + 1) / 2) * p.num_heads * p.batch;
+  if (p.seqlen_q > kBM && pair_items >= 148 && !env_int("VATTN_PREFILL_SINGLE", 0)) {
+    const size_t smem = sizeof(Prefill2KernelSmem) + 1024;
+    VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((L.pp.num_m_tiles + 1) / 2, p.num_heads, p.batch);
+    prefill2_tc_kernel<T><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.pp);
+  } else {
+    const size_t smem = sizeof(PrefillKernelSmem) + 1024;
+    VATTN_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(L.pp.num_m_tiles, p.num_heads, p.batch);
+    prefill_tc_kernel<T><<<grid, kThreads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.pp);
+  }
   timing_end(tslot, stream);
   count_launch();
   VATTN_CUDA(cudaGetLastError());

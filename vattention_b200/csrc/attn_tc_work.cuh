@@ -102,7 +102,7 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
       }
     } else {
       // zero-length sequence: output zeros (softmax.h:76-78 convention)
-      for (int i = threadIdx.x; i < G * kHeadDim; i += kThreads)
+      for (int i = threadIdx.x; i < G * kHeadDim; i += blockDim.x)
         reinterpret_cast<T*>(p.out + b * p.o_b + (int64_t)(h0 + i / kHeadDim) * p.o_h)[i % kHeadDim] =
             Elem<T>::from_f(0.f);
       if (p.lse && threadIdx.x < G) p.lse[(int64_t)b * p.num_heads + h0 + threadIdx.x] = INFINITY;
@@ -126,10 +126,10 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
   {
     // zero Q and P^T (rows >= G must stay zero), then stage this group's query heads
     uint32_t* z = reinterpret_cast<uint32_t*>(sm.q);
-    for (int i = threadIdx.x; i < (int)(sizeof(sm.q) + sizeof(sm.p)) / 4; i += kThreads) z[i] = 0;
+    for (int i = threadIdx.x; i < (int)(sizeof(sm.q) + sizeof(sm.p)) / 4; i += blockDim.x) z[i] = 0;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < G * (kHeadDim / 8); i += kThreads) {
+  for (int i = threadIdx.x; i < G * (kHeadDim / 8); i += blockDim.x) {
     const int g = i / (kHeadDim / 8), c8 = i % (kHeadDim / 8);  // 16-byte chunk c8 of head g
     const uint4 v = *reinterpret_cast<const uint4*>(p.q + b * p.q_b + (int64_t)(h0 + g) * p.q_h + c8 * 16);
     *reinterpret_cast<uint4*>(sm.q[c8 >> 3] + sw128_off(g, (c8 & 7) * 8)) = v;
@@ -201,7 +201,7 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
         if (j + 2 < n) issue_qk(j + 2);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {  // (a 384-thread CTA leaves warps 8-11 idle here)
     // ================================================= softmax / accumulate ====
     const int t = threadIdx.x - 128;  // key index inside a tile for S^T, head dim for O^T
     const int sw = warp - 4;          // TMEM lane quadrant of this warp
@@ -513,7 +513,7 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
         if (j + 2 < n) issue_qk(j + 2);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ==================================================== softmax / epilogue ====
     const int i = threadIdx.x - 128;  // query row inside the block == TMEM lane
     const int sw = warp - 4;
@@ -620,6 +620,235 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
       }
     }
     if (p.lse && i < rows)
+      p.lse[((int64_t)b * p.num_heads + h) * p.seqlen_q + qi] =
+          l > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+}
+
+
+// ============================================================== prefill, 2 row blocks ====
+// Two 128-row query blocks of the same (batch, head) per CTA, each with its own softmax
+// warpgroup, sharing every K/V tile (FlashAttention-4's ping-pong): while one warpgroup is in its
+// exponentials the tensor core runs the other block's QK^T / PV, so the softmax latency of one
+// block is hidden behind the MMAs of the other, and each staged K/V tile feeds twice the FLOPs.
+// TMEM: S0 | S1 | O0 | O1 (128 columns each); P_t is written in place over the first 64 columns of
+// S_t (16-bit packed) once they have been consumed, and the next QK^T into S_t is issued after
+// PV_t in program order (tcgen05.mma executes in issue order).
+constexpr int kPrefill2Threads = 384;
+constexpr int kPrefill2Stages = 4;
+constexpr uint32_t kCol2S = 0, kCol2O = 256;  // S_t at kCol2S + 128 t, O_t at kCol2O + 128 t
+
+struct __align__(1024) Prefill2Smem {
+  uint8_t q[2][kTile * kHeadDim * 2];
+  uint8_t ring[kPrefill2Stages][kTileBytes];
+};
+
+template <typename T>
+__device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
+                              const PrefillParams& p, Prefill2Smem& sm, TcBarriers& bar, uint32_t tmem,
+                              int mt2, int h, int b, bool barriers_live) {
+  constexpr int kStages = kPrefill2Stages;
+  constexpr int kBM = kTile, kBN = kTile, kD = kHeadDim;
+  const int hkv = h / p.group;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = p.cache_batch_idx ? p.cache_batch_idx[b] : b;
+  const int lk = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + p.seqlen_new;
+  const int shift = lk - p.seqlen_q;
+  // per block t: first row, valid rows, number of key tiles
+  int m0[2], rows[2], nt[2];
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    m0[t] = (mt2 * 2 + t) * kBM;
+    rows[t] = min(kBM, p.seqlen_q - m0[t]);
+    int kv_end = lk;
+    if (p.causal) kv_end = min(lk, m0[t] + rows[t] + shift);
+    if (kv_end < 0 || rows[t] <= 0) kv_end = 0;
+    nt[t] = (kv_end + kBN - 1) / kBN;
+  }
+  const int n = max(nt[0], nt[1]);  // key tiles to stage (block 1 sees at least as many as block 0)
+
+  if (threadIdx.x == 0) {
+    mbar_reinit(&bar.q_full, 1, barriers_live);
+    for (int s = 0; s < kStages; s++) {
+      mbar_reinit(&bar.full[s], 1, barriers_live);
+      mbar_reinit(&bar.empty[s], 1, barriers_live);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_reinit(&bar.s_full[i], 1, barriers_live);
+      mbar_reinit(&bar.p_ready[i], 128, barriers_live);
+      mbar_reinit(&bar.o_full[i], 1, barriers_live);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // =========================================================== TMA producer ====
+    if (lane == 0 && n > 0) {
+      mbar_expect_tx(&bar.q_full, 2 * kBM * kD * 2);
+      tma_load_5d(sm.q[0], qmap, &bar.q_full, 0, m0[0], 0, h, b);
+      tma_load_5d(sm.q[1], qmap, &bar.q_full, 0, m0[1], 0, h, b);  // rows past seqlen_q arrive as zeros
+      // consumption order K0 V0 K1 V1 ...: position 2j is K_j, 2j+1 is V_j
+      for (int pos = 0; pos < 2 * n; pos++) {
+        const int s = pos % kStages;
+        mbar_wait(&bar.empty[s], ((pos / kStages) & 1) ^ 1);
+        mbar_expect_tx(&bar.full[s], kTileBytes);
+        tma_load_5d(sm.ring[s], (pos & 1) ? vmap : kmap, &bar.full[s], 0, (pos >> 1) * kBN, 0, hkv, slot);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer ====
+    if (lane == 0 && n > 0) {
+      mbar_wait(&bar.q_full, 0);
+      auto wait_slot = [&](int pos) {
+        mbar_wait(&bar.full[pos % kStages], (pos / kStages) & 1);
+        tc_fence_after();
+        return smem_u32(sm.ring[pos % kStages]);
+      };
+      auto issue_qk = [&](int t, int j, uint32_t k0) {
+        const uint32_t q_addr = smem_u32(sm.q[t]);
+#pragma unroll
+        for (int ks = 0; ks < kD / 16; ks++) {
+          const uint32_t off = (ks >> 2) * (128 * 128) + (ks & 3) * 32;
+          umma_ss(tmem + kCol2S + t * kBN, make_smem_desc(q_addr + off, 16, 1024, kLayoutSw128),
+                  make_smem_desc(k0 + off, 16, 1024, kLayoutSw128), p.idesc_qk, ks > 0);
+        }
+        umma_commit(&bar.s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j, uint32_t v0) {
+        mbar_wait(&bar.p_ready[t], j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < kBN / 16; ks++)
+          umma_ts(tmem + kCol2O + t * kD, tmem + kCol2S + t * kBN + ks * 8,
+                  make_smem_desc(v0 + ks * (16 * 128), p.v_lbo, p.v_sbo, kLayoutSw128), p.idesc_pv,
+                  (j > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&bar.o_full[t]);  // completes phase j of block t
+      };
+      // prologue: S_t(0) for both blocks
+      {
+        const uint32_t k0 = wait_slot(0);
+        if (nt[0] > 0) issue_qk(0, 0, k0);
+        if (nt[1] > 0) issue_qk(1, 0, k0);
+        umma_commit(&bar.empty[0]);
+      }
+      for (int j = 0; j < n; j++) {
+        const uint32_t v0 = wait_slot(2 * j + 1);
+        uint32_t k1 = 0;
+        const bool more = j + 1 < n;
+        // block 0: PV(j) then the next QK^T, which overwrites S0/P0 only after PV0(j) in order
+        if (j < nt[0]) issue_pv(0, j, v0);
+        if (more) {
+          k1 = wait_slot(2 * j + 2);
+          if (j + 1 < nt[0]) issue_qk(0, j + 1, k1);
+        }
+        if (j < nt[1]) issue_pv(1, j, v0);
+        umma_commit(&bar.empty[(2 * j + 1) % kStages]);  // V_j consumed by both blocks
+        if (more) {
+          if (j + 1 < nt[1]) issue_qk(1, j + 1, k1);
+          umma_commit(&bar.empty[(2 * j + 2) % kStages]);  // K_{j+1} consumed by both blocks
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ==================================================== softmax / epilogue ====
+    const int t = (warp - 4) >> 2;            // which row block this warpgroup owns
+    const int i = (threadIdx.x - 128) & 127;  // query row inside the block == TMEM lane
+    const int sw = warp & 3;
+    const uint32_t lane_base = (uint32_t)(sw * 32) << 16;
+    const int qi = m0[t] + i;
+    const int my_n = nt[t];
+    int limit = lk - 1;
+    if (p.causal) limit = min(limit, qi + shift);
+    float m_ref = -INFINITY, l = 0.f;
+    const uint32_t s_addr = tmem + lane_base + kCol2S + t * kBN;
+    const uint32_t o_addr = tmem + lane_base + kCol2O + t * kD;
+
+    for (int j = 0; j < my_n; j++) {
+      mbar_wait(&bar.s_full[t], j & 1);
+      tc_fence_after();
+      const int key0 = j * kBN;
+      const bool need_mask = key0 + kBN - 1 > limit;
+      const bool warp_mask = __any_sync(0xffffffffu, need_mask);
+      float mx = warp_mask ? tile_row_max<true>(s_addr, key0, limit) : tile_row_max<false>(s_addr, key0, limit);
+      mx *= p.scale_log2;
+      float alpha = 1.f;
+      bool grow = mx > m_ref + kRescaleThreshold;
+      if (m_ref == -INFINITY && mx > -INFINITY) grow = true;
+      if (grow) {
+        alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - mx);
+        m_ref = mx;
+      }
+      if (__any_sync(0xffffffffu, grow) && j > 0) {
+        // S_t(j) is ready, so PV_t(j-1) -- issued before this tile's QK^T -- has retired
+        mbar_wait(&bar.o_full[t], (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < kD; c += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(o_addr + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+          tmem_st_x32(o_addr + c, r);
+        }
+        tmem_wait_st();
+      }
+      l *= alpha;
+      const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
+      // P_t(j) overwrites the already consumed low half of S_t (in place)
+      l += warp_mask ? tile_exp_store<T, true>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit)
+                     : tile_exp_store<T, false>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit);
+      tmem_wait_st();
+      if ((j + 1) * kBN > lk) {
+        const int pv = 2 * j + 1;
+        mbar_wait(&bar.full[pv % kStages], (pv / kStages) & 1);
+        // both warpgroups may reach the tail tile: zeroing the same rows twice is harmless
+        if (key0 + i >= lk) {
+          uint8_t* vt = sm.ring[pv % kStages];
+#pragma unroll
+          for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+              *reinterpret_cast<uint4*>(vt + a * (kBN * 128) + i * 128 + c * 16) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      mbar_arrive(&bar.p_ready[t]);
+    }
+
+    if (my_n > 0) {
+      mbar_wait(&bar.o_full[t], (my_n - 1) & 1);  // phases <= my_n-2 are known complete (see above)
+      tc_fence_after();
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    char* orow = p.out + b * p.o_b + (int64_t)qi * p.o_r + (int64_t)h * p.o_h;
+#pragma unroll
+    for (int c = 0; c < kD; c += 32) {
+      uint32_t r[32];
+      if (my_n > 0) {
+        tmem_ld_x32(o_addr + c, r);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; e++) r[e] = 0;
+      }
+      if (i < rows[t]) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          o.x = Elem<T>::from_f2(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+          o.y = Elem<T>::from_f2(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
+          o.z = Elem<T>::from_f2(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
+          o.w = Elem<T>::from_f2(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + (c + e) * 2) = o;
+        }
+      }
+    }
+    if (p.lse && i < rows[t])
       p.lse[((int64_t)b * p.num_heads + h) * p.seqlen_q + qi] =
           l > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : INFINITY;
   }
