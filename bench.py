@@ -128,7 +128,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from vattention_b200 import attention as att
     from vattention_b200 import vattention as va
-    from vattention_b200.tp import HeadShard, HeadShardedAttention
+    from vattention_b200.tp import HeadShard, HeadShardedAttention, HeadShardedAttentionPeer
 
     shard = HeadShard(rank, world, HQ, HKV, D)
     hq, hkv = shard.heads_per_rank, shard.kv_heads_per_rank
@@ -159,7 +159,13 @@ def run_ours(args):
     kn = torch.randn(LAYERS, BATCH, 1, hkv, D, device=dev, generator=g).to(DTYPE)
     vn = torch.randn(LAYERS, BATCH, 1, hkv, D, device=dev, generator=g).to(DTYPE)
     w_o = (torch.randn(hq * D, HIDDEN, device=dev, generator=g) * 0.02).to(DTYPE) if world > 1 else None
-    tp_attn = HeadShardedAttention(shard, w_o, att.flash_attn_with_kvcache) if world > 1 else None
+    tp_attn = None
+    if world > 1:
+        # the o_proj all-reduce: our one-shot kernel over NVLink peer memory (default) or NCCL
+        if args.tp_collective == "peer":
+            tp_attn = HeadShardedAttentionPeer(shard, w_o, att.flash_attn_with_kvcache, max_tokens=BATCH)
+        else:
+            tp_attn = HeadShardedAttention(shard, w_o, att.flash_attn_with_kvcache)
     scale = D ** -0.5
     sink = torch.zeros(1, device=dev, dtype=torch.float32)
 
@@ -295,6 +301,9 @@ def run_ours(args):
             "config": {"workload": "decode32k", "shapes": f"B{BATCH} Hq{HQ} Hkv{HKV} D{D} L{LAYERS} ctx{CTX}",
                        "backend": "fa_vattn_2mb (vAttention virtual tensors, 2 MiB pages, step_async)",
                        "resident_layers": n_res, "parallelism": f"tp{world}" if world > 1 else "single",
+                       "collective": (f"o_proj all-reduce [64,{HIDDEN}] bf16 per layer-call: " + (
+                           "one-shot kernel over NVLink peer memory (csrc/tp_allreduce.cu)"
+                           if args.tp_collective == "peer" else "NCCL")) if world > 1 else None,
                        "l2": "each layer-call streams 8.6 GB of K/V (>> 126 MB L2); no flush needed",
                        "ms_per_layer_call": round(ms / K / LAYERS, 4)},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
@@ -434,6 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "fa_vattn"])
     ap.add_argument("--resident-layers", type=int, default=4)
+    ap.add_argument("--tp-collective", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=2)

@@ -251,6 +251,16 @@ int vattn_cache_flat(const void* key, const void* value, void* k_cache, void* v_
  * Host tensors must be densely packed ([batch, seqlen, heads, dim]).        */
 int vattn_fwd_kvcache_host(const vattn_fwd_params_t* p, void* stream);
 
+/* One-shot all-reduce(sum) over NVLink peer memory for the head-sharded attention block: the
+ * only collective on the path (the o_proj output all-reduce, tensor_parallel/layers.py:448-451 ->
+ * mappings.py:16-26, NCCL in the reference).  peer_partial_ptrs[r] / peer_flag_ptrs[r] are the
+ * addresses, in THIS process, of rank r's partial buffer [n_elems] and flag array [world] inside a
+ * symmetric (peer-mapped) allocation; the caller alternates two such buffer/flag sets on
+ * consecutive calls and passes a strictly increasing `epoch` (same on all ranks).  Writes the sum
+ * to `out` (local).  See csrc/tp_allreduce.cu for the protocol. */
+int vattn_allreduce_oneshot(const uint64_t* peer_partial_ptrs, const uint64_t* peer_flag_ptrs, void* out,
+                            int64_t n_elems, int dtype, int rank, int world, uint32_t epoch, void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's
  * `gpu_launches` counts from here) */
 uint64_t vattn_launch_count(void);

@@ -85,3 +85,78 @@ class HeadShardedAttention:
         if self.shard.world > 1:
             dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
         return partial
+
+
+class PeerAllReduce:
+    """The all-reduce of the row-parallel o_proj output done by our own kernel over NVLink peer
+    memory (csrc/tp_allreduce.cu) instead of NCCL: every rank's partial lives in a symmetric
+    allocation (torch.distributed._symmetric_memory supplies the peer mappings -- plumbing), the
+    o_proj GEMM writes straight into it and one kernel sums all ranks' partials out of peer memory.
+
+    Usage per layer-call:   buf = ar.partial_buffer(tokens)   # view of this call's slot
+                            torch.matmul(x, w_o_shard, out=buf)
+                            y = ar.reduce(tokens)             # [tokens, hidden], local tensor
+    """
+
+    def __init__(self, hidden: int, max_tokens: int, dtype: torch.dtype, device: torch.device,
+                 group: Optional[dist.ProcessGroup] = None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("PeerAllReduce supports up to 8 ranks (one NVSwitch domain)")
+        self.hidden, self.max_tokens, self.dtype, self.device = hidden, max_tokens, dtype, device
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        self.slot_bytes = (max_tokens * hidden * itemsize + 255) // 256 * 256
+        self.flag_bytes = 256
+        total = 2 * self.slot_bytes + 2 * self.flag_bytes
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group.group_name)
+        dist.barrier(self.group)          # every rank's flags are zero before anyone publishes
+        self.base_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.epoch = 0
+        self.out = torch.empty(max_tokens, hidden, dtype=dtype, device=device)
+        self._dt = {torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}[dtype]
+
+    def partial_buffer(self, tokens: int) -> torch.Tensor:
+        """This call's slot of the symmetric buffer as a [tokens, hidden] tensor (GEMM output)."""
+        parity = (self.epoch + 1) & 1
+        raw = self.buf[parity * self.slot_bytes:(parity + 1) * self.slot_bytes]
+        return raw.view(self.dtype)[: tokens * self.hidden].view(tokens, self.hidden)
+
+    def reduce(self, tokens: int) -> torch.Tensor:
+        C, lib = self._C, self._lib.lib
+        self.epoch += 1
+        parity = self.epoch & 1
+        parts = (C.c_uint64 * self.world)(*[b + parity * self.slot_bytes for b in self.base_ptrs])
+        flags = (C.c_uint64 * self.world)(*[b + 2 * self.slot_bytes + parity * self.flag_bytes
+                                            for b in self.base_ptrs])
+        out = self.out[:tokens]
+        self._lib.check(lib.vattn_allreduce_oneshot(
+            parts, flags, out.data_ptr(), tokens * self.hidden, self._dt, self.rank, self.world,
+            self.epoch, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
+
+
+class HeadShardedAttentionPeer(HeadShardedAttention):
+    """HeadShardedAttention whose collective is PeerAllReduce (GEMM output lands in peer-visible
+    memory, one reduction kernel reads every rank's partial over NVLink)."""
+
+    def __init__(self, shard: HeadShard, w_o_shard: torch.Tensor, attn_fn, max_tokens: int,
+                 group: Optional[dist.ProcessGroup] = None):
+        super().__init__(shard, w_o_shard, attn_fn, group)
+        self.ar = PeerAllReduce(w_o_shard.shape[1], max_tokens, w_o_shard.dtype, w_o_shard.device, group)
+
+    def forward(self, q_shard: torch.Tensor, *attn_args, **attn_kwargs) -> torch.Tensor:
+        out = self.attn_fn(q_shard, *attn_args, **attn_kwargs)
+        flat = out.reshape(out.shape[0] * out.shape[1], -1)
+        tokens = flat.shape[0]
+        torch.matmul(flat, self.w_o, out=self.ar.partial_buffer(tokens))
+        return self.ar.reduce(tokens)
