@@ -191,3 +191,57 @@ def test_async_overlap_stats_and_fence():
     assert s1["critical_path_ns"] < s0["critical_path_ns"]
     va.step([0] * 8, True)          # eager reclaim: unmap everything behind the fence
     assert va.get_state()["mapped_pages"] == [0] * 8
+
+
+def test_megacache_tensor_core_path_respects_unmapped_pages():
+    """Megacache views have a row pitch of L*Hkv*D*2 bytes (here 32 KB -> 64 tokens per 2 MB page),
+    so a 128-row TMA box would run past a request's mapped prefix.  The tensor-core kernels fetch
+    the last tile in 64-row boxes instead; this test would die with an illegal address otherwise.
+    Decode (append) and chunked prefill both read straight from the virtual tensors."""
+    L, Hkv, D, Hq, B, ctx = 32, 4, 128, 16, 4, 8192
+    dtype = torch.bfloat16
+    k_mega, v_mega = va.init_kvcache(L, Hkv, D, B, ctx, 0, dtype, 2 * MB, True)
+    assert va.get_config()["tokens_per_page"] == 64
+    va.reserve_physical_pages(512 * MB)
+    lens_now = [700, 0, 130, 65]
+    va.step(lens_now, True)
+    assert va.get_state()["mapped_pages"] == [11, 0, 3, 2]
+    layer = 5
+    kc, vc = k_mega[:, :, layer], v_mega[:, :, layer]
+    g = torch.Generator().manual_seed(5)
+    host = {}
+    for r, n in enumerate(lens_now):
+        if n:
+            k = torch.randn(n, Hkv, D, generator=g).to(dtype)
+            v = torch.randn(n, Hkv, D, generator=g).to(dtype)
+            host[r] = (k, v)
+            att.cache_flat(k.cuda(), v.cuda(), kc[r], vc[r], "auto")
+    # decode: one new token per active sequence; lengths grow by one (still inside the mapped pages)
+    rids = [0, 2, 3]
+    va.step([n + 1 if n else 0 for n in lens_now], True)
+    q = torch.randn(3, 1, Hq, D, generator=g).to(dtype)
+    kn = torch.randn(3, 1, Hkv, D, generator=g).to(dtype)
+    vn = torch.randn(3, 1, Hkv, D, generator=g).to(dtype)
+    seqlens = torch.tensor([lens_now[r] for r in rids], dtype=torch.int32)
+    idx = torch.tensor(rids, dtype=torch.int32)
+    max_len = max(lens_now) + 1
+    out = att.flash_attn_with_kvcache(q.cuda(), kc[:, :max_len], vc[:, :max_len], kn.cuda(), vn.cuda(),
+                                      cache_seqlens=seqlens.cuda(), cache_batch_idx=idx.cuda(), causal=True,
+                                      impl="tc")
+    torch.cuda.synchronize()
+    kref = torch.zeros(B, max_len, Hkv, D, dtype=dtype)
+    vref = torch.zeros(B, max_len, Hkv, D, dtype=dtype)
+    for r, (k, v) in host.items():
+        kref[r, :k.shape[0]], vref[r, :k.shape[0]] = k, v
+    want = ref.attn_with_kvcache_ref(q, kref, vref, kn, vn, seqlens, idx, causal=True)
+    scale = want.float().abs().max().item()
+    assert (out.float().cpu() - want.float()).abs().max().item() <= 3e-3 * scale + 2 ** -7 * scale
+    # chunked prefill of request 0: 96 new queries over its 701 cached tokens (total stays 701)
+    qp = torch.randn(1, 96, Hq, D, generator=g).to(dtype)
+    total = torch.tensor([701], dtype=torch.int32)
+    outp = att.flash_attn_with_kvcache(qp.cuda(), kc[0:1], vc[0:1], cache_seqlens=total.cuda(), causal=True,
+                                       impl="tc")
+    torch.cuda.synchronize()
+    wantp = ref.attn_with_kvcache_ref(qp, kref[0:1], vref[0:1], cache_seqlens=total, causal=True)
+    scale = wantp.float().abs().max().item()
+    assert (outp.float().cpu() - wantp.float()).abs().max().item() <= 3e-3 * scale + 2 ** -7 * scale

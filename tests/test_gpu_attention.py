@@ -358,3 +358,35 @@ def test_pod_fused_many_items_matches_oracle(dtype):
                                         causal=True)
     assert torch.equal(out_p, sep_p)
     assert torch.equal(out_d, sep_d)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_wide_pitch_views_take_the_tensor_core_path(dtype):
+    """Row pitch 32 KB (a megacache-shaped view, 64 rows per 2 MB): the last tile of every sequence
+    is fetched with 64-row tail boxes.  impl='tc' fails loudly if the path were refused."""
+    B, S, L, Hkv, D, Hq = 2, 900, 32, 4, 128, 8
+    g = torch.Generator().manual_seed(31)
+    kmega = torch.randn(B, S, L, Hkv, D, generator=g).to(dtype)
+    vmega = torch.randn(B, S, L, Hkv, D, generator=g).to(dtype)
+    layer = 7
+    kd, vd = kmega.to(DEV), vmega.to(DEV)
+    kc, vc = kd[:, :, layer], vd[:, :, layer]
+    assert kc.stride(1) * 2 == 32768
+    # decode with append
+    q = torch.randn(B, 1, Hq, D, generator=g).to(dtype)
+    kn = torch.randn(B, 1, Hkv, D, generator=g).to(dtype)
+    vn = torch.randn(B, 1, Hkv, D, generator=g).to(dtype)
+    lens = torch.tensor([899, 450], dtype=torch.int32)
+    kref, vref = kmega[:, :, layer].clone(), vmega[:, :, layer].clone()
+    want = ref.attn_with_kvcache_ref(q, kref, vref, kn, vn, lens, causal=True)
+    out = att.flash_attn_with_kvcache(q.to(DEV), kc, vc, kn.to(DEV), vn.to(DEV), cache_seqlens=lens.to(DEV),
+                                      causal=True, impl="tc")
+    close(out, want, dtype)
+    assert torch.equal(kc.cpu(), kref)
+    # chunked prefill, both one and two row blocks per CTA
+    for Sq in (100, 300):
+        qp = torch.randn(B, Sq, Hq, D, generator=g).to(dtype)
+        lens_p = torch.tensor([777, 333], dtype=torch.int32)
+        want = ref.attn_with_kvcache_ref(qp, kref, vref, cache_seqlens=lens_p, causal=True)
+        out = att.flash_attn_with_kvcache(qp.to(DEV), kc, vc, cache_seqlens=lens_p.to(DEV), causal=True, impl="tc")
+        close(out, want, dtype)

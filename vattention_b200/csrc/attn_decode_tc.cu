@@ -46,6 +46,7 @@ struct __align__(1024) DecodeKernelSmem {
 template <typename T, int GP>
 __global__ void __launch_bounds__(kThreads, 2)
 decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
+                 const __grid_constant__ CUtensorMap kmap_tail, const __grid_constant__ CUtensorMap vmap_tail,
                  const DecodeTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   DecodeKernelSmem& sm =
@@ -63,7 +64,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  decode_work<T, GP, kStages>(&kmap, &vmap, p, sm.data, sm.bar, tmem, blockIdx.x, blockIdx.y, blockIdx.z, false);
+  decode_work<T, GP, kStages>(&kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, blockIdx.x,
+                              blockIdx.y, blockIdx.z, false);
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, kDecodeTmemCols);
 }
@@ -106,7 +108,7 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
     // shared between them; the attribute call is idempotent and cheap, set it every time
     VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tslot = timing_begin(stream);
-    kernel<<<grid, kThreads, smem, stream>>>(L.kmap, L.vmap, L.dp);
+    kernel<<<grid, kThreads, smem, stream>>>(L.kmap, L.vmap, L.kmap_tail, L.vmap_tail, L.dp);
     timing_end(tslot, stream);
   };
   if (group <= 4) launch(decode_tc_kernel<T, 4>);
@@ -150,6 +152,13 @@ void build_decode_tc(const vattn_fwd_params_t& p, void* ws, DecodeTcLaunch* out)
                                   p.k_head_stride * eb, p.k_batch_stride * eb, kTile);
   out->vmap = make_headdim128_map(p.v_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.v_row_stride * eb,
                                   p.v_head_stride * eb, p.v_batch_stride * eb, kTile);
+  // tail boxes: rows per box small enough to stay inside a mapped page (tma_desc.h)
+  const int rk = safe_tail_rows(p.k_row_stride * eb), rv = safe_tail_rows(p.v_row_stride * eb);
+  dp.tail_rows = rk < rv ? rk : rv;
+  out->kmap_tail = make_headdim128_map(p.k_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.k_row_stride * eb,
+                                       p.k_head_stride * eb, p.k_batch_stride * eb, dp.tail_rows, 1);
+  out->vmap_tail = make_headdim128_map(p.v_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.v_row_stride * eb,
+                                       p.v_head_stride * eb, p.v_batch_stride * eb, dp.tail_rows, 1);
 }
 
 bool decode_tc_supported(const vattn_fwd_params_t& p, std::string* why) {
@@ -162,11 +171,11 @@ bool decode_tc_supported(const vattn_fwd_params_t& p, std::string* why) {
   if (p.head_dim != kHeadDim) return no("head_dim != 128");
   if (p.num_heads / p.num_kv_heads > kNPad) return no("GQA group > 16");
   if (p.seqlen_k < 1) return no("empty cache");
-  // a 128-row TMA box must never straddle into an unmapped 2 MB page: the row pitch has to
-  // divide 16 KB so that tokens_per_page is a multiple of 128 (megacache views fail this)
-  const int64_t pitch_k = p.k_row_stride * 2, pitch_v = p.v_row_stride * 2;
-  if (pitch_k <= 0 || pitch_v <= 0 || 16384 % pitch_k != 0 || 16384 % pitch_v != 0)
-    return no("row pitch does not divide 16 KB (TMA tile could cross an unmapped page)");
+  // a TMA box must never reach into an unmapped 2 MB page: full 128-row boxes need the row pitch
+  // to divide 16 KB; otherwise (megacache views) the last tile of a sequence is fetched in smaller
+  // boxes that divide tokens_per_page (safe_tail_rows)
+  if (safe_tail_rows(p.k_row_stride * 2) == 0 || safe_tail_rows(p.v_row_stride * 2) == 0)
+    return no("row pitch neither divides 16 KB nor divides 2 MB into >= 8-row pages");
   if ((p.k_head_stride * 2) % 16 || (p.k_batch_stride * 2) % 16 || (p.v_head_stride * 2) % 16 ||
       (p.v_batch_stride * 2) % 16)
     return no("strides not 16-byte multiples");

@@ -55,7 +55,9 @@ template <typename T, int GP>
 __global__ void __launch_bounds__(kPrefill2Threads, 1)
 pod_tc_kernel(const __grid_constant__ CUtensorMap qmap_p, const __grid_constant__ CUtensorMap kmap_p,
               const __grid_constant__ CUtensorMap vmap_p, const __grid_constant__ CUtensorMap kmap_d,
-              const __grid_constant__ CUtensorMap vmap_d, const PrefillParams pp, const DecodeTcParams dp,
+              const __grid_constant__ CUtensorMap vmap_d, const __grid_constant__ CUtensorMap kt_p,
+              const __grid_constant__ CUtensorMap vt_p, const __grid_constant__ CUtensorMap kt_d,
+              const __grid_constant__ CUtensorMap vt_d, const PrefillParams pp, const DecodeTcParams dp,
               const PodSched sch) {
   extern __shared__ uint8_t smem_raw[];
   PodSmem& sm = *reinterpret_cast<PodSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -104,14 +106,14 @@ pod_tc_kernel(const __grid_constant__ CUtensorMap qmap_p, const __grid_constant_
       const long long rem = np0 / sch.prefill_items_per_head;
       const int h = (int)(rem % pp.num_heads), b = (int)(rem / pp.num_heads);
       if (sch.prefill_blocks == 2)
-        prefill2_work<T>(&qmap_p, &kmap_p, &vmap_p, pp, sm.u.prefill2, sm.bar, tmem, mi, h, b, true);
+        prefill2_work<T>(&qmap_p, &kmap_p, &vmap_p, &kt_p, &vt_p, pp, sm.u.prefill2, sm.bar, tmem, mi, h, b, true);
       else
-        prefill_work<T>(&qmap_p, &kmap_p, &vmap_p, pp, sm.u.prefill, sm.bar, tmem, mi, h, b, true);
+        prefill_work<T>(&qmap_p, &kmap_p, &vmap_p, &kt_p, &vt_p, pp, sm.u.prefill, sm.bar, tmem, mi, h, b, true);
     } else {
       const long long d = t - np0;  // decode item: chunk fastest, then kv head, then batch
       const int chunk = (int)(d % dp.num_chunks);
       const long long r = d / dp.num_chunks;
-      decode_work<T, GP, kPodDecodeStages>(&kmap_d, &vmap_d, dp, sm.u.decode, sm.bar, tmem, chunk,
+      decode_work<T, GP, kPodDecodeStages>(&kmap_d, &vmap_d, &kt_d, &vt_d, dp, sm.u.decode, sm.bar, tmem, chunk,
                                            (int)(r % dp.num_kv_heads), (int)(r / dp.num_kv_heads), true);
     }
   }
@@ -146,7 +148,8 @@ void launch_pod_t(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, 
   auto launch = [&](auto kernel) {
     VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tslot = timing_begin(stream);
-    kernel<<<grid, kPrefill2Threads, smem, stream>>>(P.qmap, P.kmap, P.vmap, Dl.kmap, Dl.vmap, P.pp, Dl.dp, sch);
+    kernel<<<grid, kPrefill2Threads, smem, stream>>>(P.qmap, P.kmap, P.vmap, Dl.kmap, Dl.vmap, P.kmap_tail,
+                                                     P.vmap_tail, Dl.kmap_tail, Dl.vmap_tail, P.pp, Dl.dp, sch);
     timing_end(tslot, stream);
   };
   if (group <= 4) launch(pod_tc_kernel<T, 4>);

@@ -42,7 +42,8 @@ struct __align__(1024) PrefillKernelSmem {
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
-                  const __grid_constant__ CUtensorMap vmap, const PrefillParams p) {
+                  const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap kmap_tail,
+                  const __grid_constant__ CUtensorMap vmap_tail, const PrefillParams p) {
   extern __shared__ uint8_t smem_raw[];
   PrefillKernelSmem& sm =
       *reinterpret_cast<PrefillKernelSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,7 +63,8 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constan
   const uint32_t tmem = sm.tmem_base;
   // heavy (late) row blocks first: under a causal mask they own the most key tiles
   const int mt = p.num_m_tiles - 1 - blockIdx.x;
-  prefill_work<T>(&qmap, &kmap, &vmap, p, sm.data, sm.bar, tmem, mt, blockIdx.y, blockIdx.z, false);
+  prefill_work<T>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, mt, blockIdx.y,
+                  blockIdx.z, false);
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
@@ -77,7 +79,8 @@ struct __align__(1024) Prefill2KernelSmem {
 template <typename T>
 __global__ void __launch_bounds__(kPrefill2Threads, 1)
 prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
-                   const __grid_constant__ CUtensorMap vmap, const PrefillParams p) {
+                   const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap kmap_tail,
+                   const __grid_constant__ CUtensorMap vmap_tail, const PrefillParams p) {
   extern __shared__ uint8_t smem_raw[];
   Prefill2KernelSmem& sm =
       *reinterpret_cast<Prefill2KernelSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,8 +99,8 @@ prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
   const int pairs = (p.num_m_tiles + 1) / 2;
-  prefill2_work<T>(&qmap, &kmap, &vmap, p, sm.data, sm.bar, tmem, pairs - 1 - blockIdx.x, blockIdx.y,
-                   blockIdx.z, false);
+  prefill2_work<T>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem,
+                   pairs - 1 - blockIdx.x, blockIdx.y, blockIdx.z, false);
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
@@ -119,12 +122,14 @@ void launch_t(const vattn_fwd_params_t& p, cudaStream_t stream) {
     const size_t smem = sizeof(Prefill2KernelSmem) + 1024;
     VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((L.pp.num_m_tiles + 1) / 2, p.num_heads, p.batch);
-    prefill2_tc_kernel<T><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.pp);
+    prefill2_tc_kernel<T><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
+                                                                    L.vmap_tail, L.pp);
   } else {
     const size_t smem = sizeof(PrefillKernelSmem) + 1024;
     VATTN_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L.pp.num_m_tiles, p.num_heads, p.batch);
-    prefill_tc_kernel<T><<<grid, kThreads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.pp);
+    prefill_tc_kernel<T><<<grid, kThreads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail, L.vmap_tail,
+                                                           L.pp);
   }
   timing_end(tslot, stream);
   count_launch();
@@ -159,6 +164,12 @@ void build_prefill_tc(const vattn_fwd_params_t& p, PrefillTcLaunch* out) {
                                   p.k_head_stride * eb, p.k_batch_stride * eb, kBN);
   out->vmap = make_headdim128_map(p.v_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.v_row_stride * eb,
                                   p.v_head_stride * eb, p.v_batch_stride * eb, kBN);
+  const int rk = safe_tail_rows(p.k_row_stride * eb), rv = safe_tail_rows(p.v_row_stride * eb);
+  pp.tail_rows = rk < rv ? rk : rv;
+  out->kmap_tail = make_headdim128_map(p.k_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.k_row_stride * eb,
+                                       p.k_head_stride * eb, p.k_batch_stride * eb, pp.tail_rows, 1);
+  out->vmap_tail = make_headdim128_map(p.v_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.v_row_stride * eb,
+                                       p.v_head_stride * eb, p.v_batch_stride * eb, pp.tail_rows, 1);
 }
 
 bool prefill_tc_supported(const vattn_fwd_params_t& p, std::string* why) {
@@ -169,9 +180,8 @@ bool prefill_tc_supported(const vattn_fwd_params_t& p, std::string* why) {
   if (env_int("VATTN_DISABLE_TC", 0)) return no("disabled by VATTN_DISABLE_TC");
   if (p.head_dim != kD) return no("head_dim != 128");
   if (p.seqlen_k < 1) return no("empty cache");
-  const int64_t pitch_k = p.k_row_stride * 2, pitch_v = p.v_row_stride * 2;
-  if (pitch_k <= 0 || pitch_v <= 0 || 16384 % pitch_k != 0 || 16384 % pitch_v != 0)
-    return no("row pitch does not divide 16 KB (TMA tile could cross an unmapped page)");
+  if (safe_tail_rows(p.k_row_stride * 2) == 0 || safe_tail_rows(p.v_row_stride * 2) == 0)
+    return no("row pitch neither divides 16 KB nor divides 2 MB into >= 8-row pages");
   const int64_t st[] = {p.q_row_stride, p.q_head_stride, p.q_batch_stride, p.k_head_stride,
                         p.k_batch_stride, p.v_head_stride, p.v_batch_stride};
   for (int64_t s : st)

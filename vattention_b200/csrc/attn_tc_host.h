@@ -8,7 +8,7 @@ namespace vattn {
 
 struct DecodeTcLaunch {
   tcwork::DecodeTcParams dp;
-  CUtensorMap kmap, vmap;
+  CUtensorMap kmap, vmap, kmap_tail, vmap_tail;
   SplitWorkspace ws;
 };
 // fills kernel parameters + TMA maps for a seqlen_q == 1 problem; `ws` receives the split partials
@@ -16,7 +16,7 @@ void build_decode_tc(const vattn_fwd_params_t& p, void* ws, DecodeTcLaunch* out)
 
 struct PrefillTcLaunch {
   tcwork::PrefillParams pp;
-  CUtensorMap qmap, kmap, vmap;
+  CUtensorMap qmap, kmap, vmap, kmap_tail, vmap_tail;
 };
 void build_prefill_tc(const vattn_fwd_params_t& p, PrefillTcLaunch* out);
 

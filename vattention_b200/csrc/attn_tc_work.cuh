@@ -39,6 +39,28 @@ __device__ __forceinline__ void mbar_reinit(uint64_t* bar, uint32_t count, bool 
   mbar_init(bar, count);
 }
 
+
+// Stage rows [row0, row0 + 128) of one (head, slot) of a K or V cache into a ring slot.  Rows at or
+// beyond `safe_rows` (the sequence length rounded up to `tail_rows`, itself a divisor of
+// tokens_per_page) may lie in unmapped virtual memory and are never requested: a tile that is
+// entirely safe is one 32 KB box; the last tile of a sequence on a layout whose pages hold fewer
+// than 128 rows (megacache views) is fetched as tail_rows-row boxes per 64-column atom.
+__device__ __forceinline__ void load_kv_tile(uint8_t* dst, const CUtensorMap* full, const CUtensorMap* tail,
+                                             uint64_t* bar, int row0, int head, int slot, int safe_rows,
+                                             int tail_rows) {
+  if (row0 + kTile <= safe_rows) {
+    mbar_expect_tx(bar, kTileBytes);
+    tma_load_5d(dst, full, bar, 0, row0, 0, head, slot);
+  } else {
+    const int nbox = (safe_rows - row0 + tail_rows - 1) / tail_rows;
+    mbar_expect_tx(bar, nbox * tail_rows * 128 * 2);
+    for (int i = 0; i < nbox; i++)
+      for (int a = 0; a < 2; a++)
+        tma_load_5d(dst + a * (kTile * 128) + i * tail_rows * 128, tail, bar, 0, row0 + i * tail_rows, a, head,
+                    slot);
+  }
+}
+
 // mbarriers of one CTA; shared by both kinds of work so that a persistent CTA alternating between
 // them re-initialises the same, never-overwritten words
 constexpr int kMaxStages = 6;
@@ -67,6 +89,7 @@ struct DecodeTcParams {
   float scale_log2;
   uint32_t idesc_qk, idesc_pv;
   uint32_t v_lbo, v_sbo;  // MN-major descriptor strides for the V tile
+  int tail_rows;          // rows per tail TMA box (128 = never needed)
 };
 
 template <int STAGES>
@@ -79,7 +102,8 @@ struct __align__(1024) DecodeSmemT {
 };
 
 template <typename T, int GP, int STAGES>
-__device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, const DecodeTcParams& p,
+__device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, const CUtensorMap* kmap_tail,
+                            const CUtensorMap* vmap_tail, const DecodeTcParams& p,
                             DecodeSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem, int chunk, int hkv,
                             int b, bool barriers_live) {
   static_assert(STAGES <= kMaxStages, "ring deeper than the barrier block");
@@ -141,18 +165,18 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
     // =========================================================== TMA producer ====
     if (lane == 0) {
       int pos = 0;
-      auto load = [&](const CUtensorMap* m, int tile) {
+      const int safe_rows = (len + p.tail_rows - 1) / p.tail_rows * p.tail_rows;
+      auto load = [&](const CUtensorMap* m, const CUtensorMap* mt, int tile) {
         const int s = pos % STAGES;
         mbar_wait(&bar.empty[s], ((pos / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&bar.full[s], kTileBytes);
-        tma_load_5d(sm.ring[s], m, &bar.full[s], 0, (tile0 + tile) * kTile, 0, hkv, slot);
+        load_kv_tile(sm.ring[s], m, mt, &bar.full[s], (tile0 + tile) * kTile, hkv, slot, safe_rows, p.tail_rows);
         pos++;
       };
-      load(kmap, 0);
-      if (n > 1) load(kmap, 1);
+      load(kmap, kmap_tail, 0);
+      if (n > 1) load(kmap, kmap_tail, 1);
       for (int j = 0; j < n; j++) {
-        load(vmap, j);
-        if (j + 2 < n) load(kmap, j + 2);
+        load(vmap, vmap_tail, j);
+        if (j + 2 < n) load(kmap, kmap_tail, j + 2);
       }
     }
   } else if (warp == 1) {
@@ -342,6 +366,7 @@ struct PrefillParams {
   float scale_log2;
   uint32_t idesc_qk, idesc_pv;
   uint32_t v_lbo, v_sbo;
+  int tail_rows;
 };
 
 struct __align__(1024) PrefillSmem {
@@ -416,6 +441,7 @@ __device__ __forceinline__ float tile_exp_store(uint32_t s_addr, uint32_t p_addr
 
 template <typename T>
 __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
+                             const CUtensorMap* kmap_tail, const CUtensorMap* vmap_tail,
                              const PrefillParams& p, PrefillSmem& sm, TcBarriers& bar, uint32_t tmem, int mt,
                              int h, int b, bool barriers_live) {
   constexpr int kStages = kPrefillStages;
@@ -454,18 +480,18 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
       mbar_expect_tx(&bar.q_full, kBM * kD * 2);
       tma_load_5d(sm.q, qmap, &bar.q_full, 0, m0, 0, h, b);
       int pos = 0;
-      auto load = [&](const CUtensorMap* m, int tile) {
+      const int safe_rows = (lk + p.tail_rows - 1) / p.tail_rows * p.tail_rows;
+      auto load = [&](const CUtensorMap* m, const CUtensorMap* mt, int tile) {
         const int s = pos % kStages;
         mbar_wait(&bar.empty[s], ((pos / kStages) & 1) ^ 1);
-        mbar_expect_tx(&bar.full[s], kTileBytes);
-        tma_load_5d(sm.ring[s], m, &bar.full[s], 0, tile * kBN, 0, hkv, slot);
+        load_kv_tile(sm.ring[s], m, mt, &bar.full[s], tile * kBN, hkv, slot, safe_rows, p.tail_rows);
         pos++;
       };
-      load(kmap, 0);
-      if (n > 1) load(kmap, 1);
+      load(kmap, kmap_tail, 0);
+      if (n > 1) load(kmap, kmap_tail, 1);
       for (int j = 0; j < n; j++) {
-        load(vmap, j);
-        if (j + 2 < n) load(kmap, j + 2);
+        load(vmap, vmap_tail, j);
+        if (j + 2 < n) load(kmap, kmap_tail, j + 2);
       }
     }
   } else if (warp == 1) {
@@ -647,6 +673,7 @@ struct __align__(1024) Prefill2Smem {
 
 template <typename T>
 __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
+                              const CUtensorMap* kmap_tail, const CUtensorMap* vmap_tail,
                               const PrefillParams& p, Prefill2Smem& sm, TcBarriers& bar, uint32_t tmem,
                               int mt2, int h, int b, bool barriers_live) {
   constexpr int kStages = kPrefill2Stages;
@@ -691,11 +718,12 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       tma_load_5d(sm.q[0], qmap, &bar.q_full, 0, m0[0], 0, h, b);
       tma_load_5d(sm.q[1], qmap, &bar.q_full, 0, m0[1], 0, h, b);  // rows past seqlen_q arrive as zeros
       // consumption order K0 V0 K1 V1 ...: position 2j is K_j, 2j+1 is V_j
+      const int safe_rows = (lk + p.tail_rows - 1) / p.tail_rows * p.tail_rows;
       for (int pos = 0; pos < 2 * n; pos++) {
         const int s = pos % kStages;
         mbar_wait(&bar.empty[s], ((pos / kStages) & 1) ^ 1);
-        mbar_expect_tx(&bar.full[s], kTileBytes);
-        tma_load_5d(sm.ring[s], (pos & 1) ? vmap : kmap, &bar.full[s], 0, (pos >> 1) * kBN, 0, hkv, slot);
+        load_kv_tile(sm.ring[s], (pos & 1) ? vmap : kmap, (pos & 1) ? vmap_tail : kmap_tail, &bar.full[s],
+                     (pos >> 1) * kBN, hkv, slot, safe_rows, p.tail_rows);
       }
     }
   } else if (warp == 1) {

@@ -15,6 +15,11 @@ namespace vattn {
 // Rows past `seq_extent` are zero-filled by the TMA unit without touching memory.
 CUtensorMap make_headdim128_map(const void* base, int64_t seq_extent, int64_t heads, int64_t slots,
                                 int64_t row_stride_bytes, int64_t head_stride_bytes,
-                                int64_t batch_stride_bytes, int box_rows);
+                                int64_t batch_stride_bytes, int box_rows, int box_atoms = 2);
+
+// rows per TMA box that can never reach past a request's mapped prefix: 128 when the row pitch
+// divides 16 KB (tokens_per_page is a multiple of 128), otherwise the largest power of two <= 128
+// dividing tokens_per_page = 2 MiB / pitch (megacache views).  0 = layout not usable with TMA.
+int safe_tail_rows(int64_t row_pitch_bytes);
 
 }  // namespace vattn
