@@ -250,6 +250,11 @@ int vattn_cache_flat(const void* key, const void* value, void* k_cache, void* v_
  * copies `out` back, all on `stream`; returns after the stream is drained.
  * Host tensors must be densely packed ([batch, seqlen, heads, dim]).        */
 int vattn_fwd_kvcache_host(const vattn_fwd_params_t* p, void* stream);
+/* Same, but returns as soon as the copies and kernels are enqueued: the result is in `out` once
+ * `stream` has been synchronised.  Staging is stream-ordered, so consecutive calls on one stream
+ * (the layers of a decode iteration) need no host synchronisation in between; the host buffers
+ * must stay untouched until the stream is drained.                                            */
+int vattn_fwd_kvcache_host_async(const vattn_fwd_params_t* p, void* stream);
 
 /* One-shot all-reduce(sum) over NVLink peer memory for the head-sharded attention block: the
  * only collective on the path (the o_proj output all-reduce, tensor_parallel/layers.py:448-451 ->

@@ -117,6 +117,7 @@ _SIGS = {
                                    C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                    C.c_int32, C.c_void_p]),
     "vattn_fwd_kvcache_host": (C.c_int, [_P(FwdParams), C.c_void_p]),
+    "vattn_fwd_kvcache_host_async": (C.c_int, [_P(FwdParams), C.c_void_p]),
     "vattn_allreduce_oneshot": (C.c_int, [_P(C.c_uint64), _P(C.c_uint64), C.c_void_p, C.c_int64, C.c_int,
                                           C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
     "vattn_launch_count": (C.c_uint64, []),

@@ -260,10 +260,12 @@ def flash_attn_with_kvcache_host(q_host: torch.Tensor, k_cache: torch.Tensor, v_
                                  cache_seqlens_host: Optional[torch.Tensor],
                                  cache_batch_idx_host: Optional[torch.Tensor], out_host: torch.Tensor,
                                  softmax_scale: Optional[float] = None, causal: bool = False,
-                                 impl: str = "auto") -> torch.Tensor:
+                                 impl: str = "auto", wait: bool = True) -> torch.Tensor:
     """Same operation with HOST (ideally pinned) q / k / v / index / out buffers and device-resident
     caches: the library copies in, runs the kernels and copies the result back, then drains the
-    stream (vattn_fwd_kvcache_host).  This is the call bench.py's `e2e` leg times."""
+    stream (vattn_fwd_kvcache_host).  wait=False enqueues only (vattn_fwd_kvcache_host_async): the
+    result is valid after the stream is synchronised, and the layers of one decode iteration can be
+    issued back to back.  This is the call bench.py's `e2e` leg times."""
     for t in (q_host, k_host, v_host, cache_seqlens_host, cache_batch_idx_host, out_host):
         if t is not None and (t.is_cuda or not t.is_contiguous()):
             raise RuntimeError("host tensors must be contiguous CPU tensors")
@@ -271,7 +273,8 @@ def flash_attn_with_kvcache_host(q_host: torch.Tensor, k_cache: torch.Tensor, v_
         softmax_scale = q_host.shape[-1] ** (-0.5)
     p = _fill_params(q_host, k_cache, v_cache, k_host, v_host, out_host, cache_seqlens_host,
                      cache_batch_idx_host, softmax_scale, causal, impl, 0, None)
-    check(lib.vattn_fwd_kvcache_host(C.byref(p), _stream(k_cache.device)))
+    fn = lib.vattn_fwd_kvcache_host if wait else lib.vattn_fwd_kvcache_host_async
+    check(fn(C.byref(p), _stream(k_cache.device)))
     return out_host
 
 

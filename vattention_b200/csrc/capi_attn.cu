@@ -307,7 +307,7 @@ int vattn_cache_flat(const void* key, const void* value, void* k_cache, void* v_
   }
 }
 
-int vattn_fwd_kvcache_host(const vattn_fwd_params_t* hp, void* stream_) {
+static int fwd_kvcache_host_impl(const vattn_fwd_params_t* hp, void* stream_, bool drain) {
   if (!hp) return VATTN_ERR_INVALID;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   try {
@@ -360,11 +360,19 @@ int vattn_fwd_kvcache_host(const vattn_fwd_params_t* hp, void* stream_) {
     p.workspace_bytes = g_stage.ws_cap;
     run_fwd(p, stream);
     VATTN_CUDA(cudaMemcpyAsync(hp->out, d_o, q_bytes, cudaMemcpyDeviceToHost, stream));
-    VATTN_CUDA(cudaStreamSynchronize(stream));
+    if (drain) VATTN_CUDA(cudaStreamSynchronize(stream));
     return VATTN_OK;
   } catch (...) {
     return translate_attn_exception();
   }
+}
+
+int vattn_fwd_kvcache_host(const vattn_fwd_params_t* hp, void* stream) {
+  return fwd_kvcache_host_impl(hp, stream, true);
+}
+
+int vattn_fwd_kvcache_host_async(const vattn_fwd_params_t* hp, void* stream) {
+  return fwd_kvcache_host_impl(hp, stream, false);
 }
 
 uint64_t vattn_launch_count(void) { return g_launch_count.load(); }
