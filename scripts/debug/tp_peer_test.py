@@ -24,7 +24,10 @@ for it in range(50):
     # exact reference: gather every rank's bf16 partial, sum in fp32, round once (what the kernel does)
     parts = [torch.empty_like(x) for _ in range(world)]
     dist.all_gather(parts, x)
-    want = torch.stack([p.float() for p in parts]).sum(0).bfloat16()
+    acc = torch.zeros_like(parts[0], dtype=torch.float32)
+    for p in parts:                      # same order as the kernel: rank 0 .. world-1, fp32
+        acc += p.float()
+    want = acc.bfloat16()
     worst = max(worst, (got.float() - want.float()).abs().max().item())
     assert torch.equal(got, want), f"rank {rank} iter {it}: mismatch {worst}"
 if rank == 0:

@@ -2,7 +2,7 @@
 // warp-shuffle softmax reductions.  This is the generic path (any seqlen_q,
 // head_dim 64/128, any GQA ratio, fp16/bf16) and the parity anchor for the
 // tcgen05 kernels; the tensor-core paths take over where the shapes allow
-// (see attn_dispatch.cu for why CUDA-core FMAs cannot sustain GQA decode at HBM
+// (see capi_attn.cu for why CUDA-core FMAs cannot sustain GQA decode at HBM
 // speed on B200).
 //
 // Semantics restated from the FA-2 fork the reference vendors:
