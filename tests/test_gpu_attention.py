@@ -354,8 +354,8 @@ def test_pod_fused_many_items_matches_oracle(dtype):
     assert torch.equal(kd.cpu(), kc_r) and torch.equal(vd.cpu(), vc_r)
     # fused == the two separate calls, bit for bit (same work functions)
     sep_p = att.flash_attn_with_kvcache(d(q_p), d(kc_p), d(vc_p), cache_seqlens=d(lens_p), causal=True)
-    sep_d = att.flash_attn_with_kvcache(d(q_d), kd, vd, cache_seqlens=d(lens_d) + 1, cache_batch_idx=d(idx),
-                                        causal=True)
+    sep_d = att.flash_attn_with_kvcache(d(q_d), kd, vd, d(kn), d(vn), cache_seqlens=d(lens_d),
+                                        cache_batch_idx=d(idx), causal=True)  # re-appends the same rows
     assert torch.equal(out_p, sep_p)
     assert torch.equal(out_d, sep_d)
 

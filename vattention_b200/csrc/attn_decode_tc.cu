@@ -20,6 +20,8 @@
 // One CTA = (chunk of <= TPC tiles, kv head, batch entry); 2 CTAs per SM, 3 x 32 KB ring each.
 // Chunks write un-normalised partials (acc, m, l) that the shared combine kernel reduces.
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "attn_common.cuh"
 #include "sm100_ptx.cuh"
@@ -100,7 +102,7 @@ template <typename T>
 void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
   const int group = p.num_heads / p.num_kv_heads;
   DecodeTcLaunch L;
-  build_decode_tc(p, ws, &L);
+  build_decode_tc(p, ws, stream, &L);
   const size_t smem = sizeof(DecodeKernelSmem) + 1024;
   dim3 grid(L.dp.num_chunks, p.num_kv_heads, p.batch);
   auto launch = [&](auto kernel) {
@@ -116,12 +118,38 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
   else launch(decode_tc_kernel<T, 16>);
   count_launch();
   VATTN_CUDA(cudaGetLastError());
-  if (L.dp.num_chunks > 1) launch_combine(p, L.dp.num_chunks, L.ws, stream);
+  // partials are reduced inside the kernel (last chunk to arrive) unless that was switched off
+  if (!L.dp.arrive && L.dp.num_chunks > 1) launch_combine(p, L.dp.num_chunks, L.ws, stream);
 }
 
 }  // namespace
 
-void build_decode_tc(const vattn_fwd_params_t& p, void* ws, DecodeTcLaunch* out) {
+// One zero-initialised counter array per stream for the in-kernel split combine ("last chunk of a
+// sequence to finish reduces the partials"); the kernel resets what it used, so there is no
+// per-call memset.  Per stream because two decodes on different streams may overlap in time.
+static int env_int_(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+int* decode_arrive_counters(cudaStream_t stream, size_t need) {
+  static std::mutex mu;
+  static std::unordered_map<cudaStream_t, std::pair<int*, size_t>> bufs;
+  std::lock_guard<std::mutex> g(mu);
+  auto& e = bufs[stream];
+  if (e.second < need) {
+    if (e.first) cudaFree(e.first);
+    const size_t n = need < 65536 ? 65536 : need;
+    VATTN_CUDA(cudaMalloc(&e.first, n * sizeof(int)));
+    VATTN_CUDA(cudaMemset(e.first, 0, n * sizeof(int)));
+    e.second = n;
+  }
+  return e.first;
+}
+
+bool decode_tc_fuses_append(const vattn_fwd_params_t& p) { return p.k_new != nullptr && p.seqlen_new == 1; }
+
+void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream, DecodeTcLaunch* out) {
   const int group = p.num_heads / p.num_kv_heads;
   const int eb = 2;
   DecodeTcParams& dp = out->dp;
@@ -136,6 +164,19 @@ void build_decode_tc(const vattn_fwd_params_t& p, void* ws, DecodeTcLaunch* out)
   dp.seqlen_new = p.k_new ? p.seqlen_new : 0;
   dp.num_heads = p.num_heads, dp.num_kv_heads = p.num_kv_heads, dp.group = group;
   dp.batch = p.batch;
+  const bool fuse = decode_tc_fuses_append(p);
+  dp.k_new = fuse ? (const char*)p.k_new : nullptr;
+  dp.v_new = fuse ? (const char*)p.v_new : nullptr;
+  dp.kn_b = p.knew_batch_stride * eb, dp.kn_h = p.knew_head_stride * eb;
+  dp.vn_b = p.vnew_batch_stride * eb, dp.vn_h = p.vnew_head_stride * eb;
+  dp.k_cache = (char*)p.k_cache, dp.v_cache = (char*)p.v_cache;
+  dp.kc_b = p.k_batch_stride * eb, dp.kc_r = p.k_row_stride * eb, dp.kc_h = p.k_head_stride * eb;
+  dp.vc_b = p.v_batch_stride * eb, dp.vc_r = p.v_row_stride * eb, dp.vc_h = p.v_head_stride * eb;
+  // split partials are reduced by combine_kernel; VATTN_DECODE_COMBINE_INKERNEL=1 lets the last chunk of
+  // a sequence to arrive do it inside the sweep instead (one launch less, but every CTA then pays a
+  // fence + atomic in its epilogue: measured 1.219 vs 1.203 ms kernel time at B64 x 32K, a wash overall)
+  static const bool inkernel = env_int_("VATTN_DECODE_COMBINE_INKERNEL", 0) != 0;
+  dp.arrive = inkernel ? decode_arrive_counters(stream, (size_t)p.batch * p.num_kv_heads) : nullptr;
   dp.tiles_per_chunk = tiles_per_chunk_for(p);
   dp.num_chunks = num_chunks_for(p);
   dp.scale_log2 = p.softmax_scale * kLog2e;

@@ -129,7 +129,7 @@ void launch_pod_t(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, 
   PrefillTcLaunch P;
   DecodeTcLaunch Dl;
   build_prefill_tc(pre, &P);
-  build_decode_tc(dec, dec_ws, &Dl);
+  build_decode_tc(dec, dec_ws, stream, &Dl);
   PodSched sch;
   sch.counter = counter;
   sch.prefill_blocks = pre.seqlen_q > kTile ? 2 : 1;
@@ -137,7 +137,7 @@ void launch_pod_t(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, 
   sch.n_prefill = (long long)sch.prefill_items_per_head * pre.num_heads * pre.batch;
   sch.n_decode = (long long)Dl.dp.num_chunks * dec.num_kv_heads * dec.batch;
   VATTN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-  launch_append_kv(dec, stream);
+  if (!decode_tc_fuses_append(dec)) launch_append_kv(dec, stream);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -157,7 +157,7 @@ void launch_pod_t(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, 
   else launch(pod_tc_kernel<T, 16>);
   count_launch();
   VATTN_CUDA(cudaGetLastError());
-  if (Dl.dp.num_chunks > 1) launch_combine(dec, Dl.dp.num_chunks, Dl.ws, stream);
+  if (!Dl.dp.arrive && Dl.dp.num_chunks > 1) launch_combine(dec, Dl.dp.num_chunks, Dl.ws, stream);
 }
 
 }  // namespace

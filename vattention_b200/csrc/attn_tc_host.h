@@ -12,7 +12,9 @@ struct DecodeTcLaunch {
   SplitWorkspace ws;
 };
 // fills kernel parameters + TMA maps for a seqlen_q == 1 problem; `ws` receives the split partials
-void build_decode_tc(const vattn_fwd_params_t& p, void* ws, DecodeTcLaunch* out);
+void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream, DecodeTcLaunch* out);
+// true when the decode kernel itself appends k_new/v_new (one new token per sequence)
+bool decode_tc_fuses_append(const vattn_fwd_params_t& p);
 
 struct PrefillTcLaunch {
   tcwork::PrefillParams pp;

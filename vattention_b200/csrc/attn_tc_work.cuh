@@ -90,6 +90,16 @@ struct DecodeTcParams {
   uint32_t idesc_qk, idesc_pv;
   uint32_t v_lbo, v_sbo;  // MN-major descriptor strides for the V tile
   int tail_rows;          // rows per tail TMA box (128 = never needed)
+  // fused append of ONE new token per sequence (NULL: none, or appended by a separate kernel):
+  // the chunk that owns the end of the sequence folds k_new/v_new in from registers and writes
+  // them to cache row cache_seqlens[b]
+  const char* k_new;
+  const char* v_new;
+  int64_t kn_b, kn_h, vn_b, vn_h;              // byte strides of k_new / v_new
+  char* k_cache;
+  char* v_cache;
+  int64_t kc_b, kc_r, kc_h, vc_b, vc_r, vc_h;  // byte strides of the caches
+  int* arrive;  // one counter per (batch, kv head): the last chunk to finish combines the partials
 };
 
 template <int STAGES>
@@ -99,6 +109,8 @@ struct __align__(1024) DecodeSmemT {
   uint8_t p[2][2][kNPad * 128];      // P^T: double buffered, 2 K-atoms of [16 rows x 64 keys]
   float wmax[2][4][kNPad];           // cross-warp tile max exchange
   float red[4][kNPad];               // final row-sum exchange
+  float red2[4][kNPad];              // q . k_new exchange (fused append)
+  int ticket;                        // arrival order of this chunk among its sequence's chunks
 };
 
 template <typename T, int GP, int STAGES>
@@ -109,29 +121,33 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
   static_assert(STAGES <= kMaxStages, "ring deeper than the barrier block");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = p.cache_batch_idx ? p.cache_batch_idx[b] : b;
-  const int len = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + p.seqlen_new;
+  const bool fused_new = p.k_new != nullptr;
+  // rows read from the cache; with a fused append the new token is NOT read back from memory
+  const int len = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + (fused_new ? 0 : p.seqlen_new);
   const int ntiles_seq = (len + kTile - 1) / kTile;
+  const int chunks_active = max(1, (ntiles_seq + p.tiles_per_chunk - 1) / p.tiles_per_chunk);
   const int tile0 = chunk * p.tiles_per_chunk;
-  const int n = min(p.tiles_per_chunk, ntiles_seq - tile0);  // tiles of this item
+  const int n = max(0, min(p.tiles_per_chunk, ntiles_seq - tile0));  // tiles of this item
+  const bool owns_new = fused_new && chunk == chunks_active - 1;
   const int G = p.group;
   const int h0 = hkv * G;
 
-  if (n <= 0) {
-    // nothing to do for this chunk: publish an empty partial so the combine skips it
-    if (p.num_chunks > 1) {
-      if (threadIdx.x < G) {
-        const int64_t base = ((int64_t)b * p.num_heads + h0 + threadIdx.x) * p.num_chunks + chunk;
-        p.ws_ml[base * 2] = -INFINITY;
-        p.ws_ml[base * 2 + 1] = 0.f;
-      }
-    } else {
-      // zero-length sequence: output zeros (softmax.h:76-78 convention)
-      for (int i = threadIdx.x; i < G * kHeadDim; i += blockDim.x)
-        reinterpret_cast<T*>(p.out + b * p.o_b + (int64_t)(h0 + i / kHeadDim) * p.o_h)[i % kHeadDim] =
-            Elem<T>::from_f(0.f);
-      if (p.lse && threadIdx.x < G) p.lse[(int64_t)b * p.num_heads + h0 + threadIdx.x] = INFINITY;
+  if (chunk >= chunks_active) {  // CTA-uniform: this chunk lies past the sequence
+    // with the separate combine kernel every slot must hold something: publish an empty partial
+    if (!p.arrive && threadIdx.x < G) {
+      const int64_t base = ((int64_t)b * p.num_heads + h0 + threadIdx.x) * p.num_chunks + chunk;
+      p.ws_ml[base * 2] = -INFINITY;
+      p.ws_ml[base * 2 + 1] = 0.f;
     }
-    return;  // CTA-uniform
+    return;
+  }
+  if (n == 0 && !owns_new) {
+    // zero-length sequence, nothing appended: output zeros (softmax.h:76-78 convention)
+    for (int i = threadIdx.x; i < G * kHeadDim; i += blockDim.x)
+      reinterpret_cast<T*>(p.out + b * p.o_b + (int64_t)(h0 + i / kHeadDim) * p.o_h)[i % kHeadDim] =
+          Elem<T>::from_f(0.f);
+    if (p.lse && threadIdx.x < G) p.lse[(int64_t)b * p.num_heads + h0 + threadIdx.x] = INFINITY;
+    return;
   }
 
   // ---------------------------------------------------------------- setup ----
@@ -172,7 +188,7 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
         load_kv_tile(sm.ring[s], m, mt, &bar.full[s], (tile0 + tile) * kTile, hkv, slot, safe_rows, p.tail_rows);
         pos++;
       };
-      load(kmap, kmap_tail, 0);
+      if (n > 0) load(kmap, kmap_tail, 0);
       if (n > 1) load(kmap, kmap_tail, 1);
       for (int j = 0; j < n; j++) {
         load(vmap, vmap_tail, j);
@@ -181,7 +197,7 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer ====
-    if (lane == 0) {
+    if (lane == 0 && n > 0) {
       int pos = 0;
       const uint32_t q_addr = smem_u32(sm.q[0]);
       auto issue_qk = [&](int j) {
@@ -312,9 +328,9 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
       tc_fence_before();
       mbar_arrive(&bar.p_ready[j & 1]);
     }
-    accumulate_o(n - 1);
+    if (n > 0) accumulate_o(n - 1);
 
-    // ---- epilogue: row sums across the 128 key-threads, then publish ----
+    // ---- epilogue: row sums across the 128 key-threads ----
     float lsum[GP];
 #pragma unroll
     for (int g = 0; g < GP; g++) lsum[g] = l_thr[g];
@@ -322,27 +338,105 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
     for (int off = 16; off >= 1; off >>= 1)
 #pragma unroll
       for (int g = 0; g < GP; g++) lsum[g] += __shfl_xor_sync(0xffffffffu, lsum[g], off);
+    float sn[GP];  // q . k_new partial sums over this thread's dim (fused append)
+    float vnew = 0.f;
+    if (owns_new) {
+      const float kd = Elem<T>::to_f(reinterpret_cast<const T*>(p.k_new + b * p.kn_b + (int64_t)hkv * p.kn_h)[t]);
+      vnew = Elem<T>::to_f(reinterpret_cast<const T*>(p.v_new + b * p.vn_b + (int64_t)hkv * p.vn_h)[t]);
+#pragma unroll
+      for (int g = 0; g < GP; g++)
+        sn[g] = g < G ? kd * Elem<T>::to_f(*reinterpret_cast<const T*>(sm.q[t >> 6] + sw128_off(g, t & 63))) : 0.f;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+        for (int g = 0; g < GP; g++) sn[g] += __shfl_xor_sync(0xffffffffu, sn[g], off);
+      // the new row goes into the cache for the following steps (nobody reads it in this launch)
+      const int64_t row = len;
+      if (t < 16)
+        *reinterpret_cast<uint4*>(p.k_cache + slot * p.kc_b + row * p.kc_r + (int64_t)hkv * p.kc_h + t * 16) =
+            *reinterpret_cast<const uint4*>(p.k_new + b * p.kn_b + (int64_t)hkv * p.kn_h + t * 16);
+      else if (t < 32)
+        *reinterpret_cast<uint4*>(p.v_cache + slot * p.vc_b + row * p.vc_r + (int64_t)hkv * p.vc_h + (t - 16) * 16) =
+            *reinterpret_cast<const uint4*>(p.v_new + b * p.vn_b + (int64_t)hkv * p.vn_h + (t - 16) * 16);
+    }
 #pragma unroll
     for (int g = 0; g < GP; g++)
-      if (lane == g) sm.red[sw][g] = lsum[g];
+      if (lane == g) {
+        sm.red[sw][g] = lsum[g];
+        if (owns_new) sm.red2[sw][g] = sn[g];
+      }
     named_bar_sync(1, 128);
+    float Lg[GP];
 #pragma unroll
     for (int g = 0; g < GP; g++) {
-      if (g >= G) continue;
-      const float L = sm.red[0][g] + sm.red[1][g] + sm.red[2][g] + sm.red[3][g];
-      const int h = h0 + g;
-      if (p.num_chunks == 1) {
-        const float inv = L > 0.f ? 1.f / L : 0.f;
-        reinterpret_cast<T*>(p.out + b * p.o_b + (int64_t)h * p.o_h)[t] = Elem<T>::from_f(acc[g] * inv);
-        if (p.lse && t == 0)
-          p.lse[(int64_t)b * p.num_heads + h] = L > 0.f ? (m_run[g] + log2f(L)) * 0.6931471805599453f : INFINITY;
-      } else {
-        const int64_t base = ((int64_t)b * p.num_heads + h) * p.num_chunks + chunk;
+      Lg[g] = sm.red[0][g] + sm.red[1][g] + sm.red[2][g] + sm.red[3][g];
+      if (owns_new) {
+        // the appended token as one more key: s = scale * q . k_new, value v_new
+        const float s_new = (sm.red2[0][g] + sm.red2[1][g] + sm.red2[2][g] + sm.red2[3][g]) * p.scale_log2;
+        const float m_fin = fmaxf(m_run[g], s_new);
+        const float a = fast_exp2(m_run[g] - m_fin);  // m_run == -inf (no cached key) -> 0
+        const float pn = fast_exp2(s_new - m_fin);
+        acc[g] = fmaf(acc[g], a, pn * vnew);
+        Lg[g] = fmaf(Lg[g], a, pn);
+        m_run[g] = m_fin;
+      }
+    }
+
+    // one chunk covers the whole sequence: final result.  Otherwise publish the partial; it is
+    // reduced either by the last chunk of the sequence to arrive (p.arrive) or by combine_kernel.
+    bool write_out = p.arrive ? chunks_active == 1 : p.num_chunks == 1;
+    if (!write_out) {
+      // publish this chunk's partial; the last chunk of the sequence to arrive reduces them all
+#pragma unroll
+      for (int g = 0; g < GP; g++) {
+        if (g >= G) continue;
+        const int64_t base = ((int64_t)b * p.num_heads + h0 + g) * p.num_chunks + chunk;
         p.ws_acc[base * kHeadDim + t] = acc[g];
         if (t == 0) {
           p.ws_ml[base * 2] = m_run[g];
-          p.ws_ml[base * 2 + 1] = L;
+          p.ws_ml[base * 2 + 1] = Lg[g];
         }
+      }
+      if (p.arrive) {
+        // CTA barrier, then ONE thread fences and takes a ticket (fences are cumulative: the
+        // partial stores of the other 127 threads are ordered before the atomic)
+        named_bar_sync(1, 128);
+        if (t == 0) {
+          __threadfence();
+          sm.ticket = atomicAdd(p.arrive + (int64_t)b * p.num_kv_heads + hkv, 1);
+        }
+        named_bar_sync(1, 128);
+      }
+      if (p.arrive && sm.ticket == chunks_active - 1) {
+        __threadfence();
+        write_out = true;
+#pragma unroll
+        for (int g = 0; g < GP; g++) {
+          if (g >= G) continue;
+          const int64_t base = ((int64_t)b * p.num_heads + h0 + g) * p.num_chunks;
+          float M = -INFINITY;
+          for (int c = 0; c < chunks_active; c++) M = fmaxf(M, __ldcg(p.ws_ml + (base + c) * 2));
+          float o = 0.f, L = 0.f;
+          for (int c = 0; c < chunks_active; c++) {
+            const float w = fast_exp2(__ldcg(p.ws_ml + (base + c) * 2) - M);
+            L = fmaf(__ldcg(p.ws_ml + (base + c) * 2 + 1), w, L);
+            o = fmaf(__ldcg(p.ws_acc + (base + c) * kHeadDim + t), w, o);
+          }
+          acc[g] = o, Lg[g] = L, m_run[g] = M;
+        }
+        if (t == 0) p.arrive[(int64_t)b * p.num_kv_heads + hkv] = 0;  // ready for the next launch
+      }
+    }
+    if (write_out) {
+#pragma unroll
+      for (int g = 0; g < GP; g++) {
+        if (g >= G) continue;
+        const int h = h0 + g;
+        const float inv = Lg[g] > 0.f ? 1.f / Lg[g] : 0.f;
+        reinterpret_cast<T*>(p.out + b * p.o_b + (int64_t)h * p.o_h)[t] = Elem<T>::from_f(acc[g] * inv);
+        if (p.lse && t == 0)
+          p.lse[(int64_t)b * p.num_heads + h] =
+              Lg[g] > 0.f ? (m_run[g] + log2f(Lg[g])) * 0.6931471805599453f : INFINITY;
       }
     }
   }

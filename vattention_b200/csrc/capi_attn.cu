@@ -26,6 +26,7 @@ void launch_simt(const vattn_fwd_params_t&, int, const SplitWorkspace&, cudaStre
 int simt_num_splits(const vattn_fwd_params_t&);
 // tensor-core paths (attn_decode_tc.cu / attn_prefill_tc.cu)
 bool decode_tc_supported(const vattn_fwd_params_t&, std::string* why);
+bool decode_tc_fuses_append(const vattn_fwd_params_t&);
 size_t decode_tc_workspace(const vattn_fwd_params_t&);
 void launch_decode_tc(const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
 bool prefill_tc_supported(const vattn_fwd_params_t&, std::string* why);
@@ -145,8 +146,10 @@ size_t workspace_for(const vattn_fwd_params_t& p, Path path) {
 void run_fwd(const vattn_fwd_params_t& p, cudaStream_t stream) {
   validate(p);
   if (p.batch == 0) return;
-  launch_append_kv(p, stream);
   const Path path = choose(p);
+  // the tensor-core decode kernel appends a single new token itself; every other case uses the
+  // separate append kernel
+  if (!(path == Path::DecodeTc && decode_tc_fuses_append(p))) launch_append_kv(p, stream);
   const size_t need = workspace_for(p, path);
   if (need > 0 && (!p.workspace || p.workspace_bytes < need))
     throw ArgError("[vattn] workspace too small: need " + std::to_string(need) + " bytes");
