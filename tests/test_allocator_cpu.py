@@ -80,7 +80,11 @@ def test_reserve_rounds_to_2L(mock_backend):
 
 def test_rejects_bad_config(mock_backend):
     with pytest.raises(RuntimeError, match="VMM granularity"):
-        va.init_kvcache(2, 2, 64, 2, 8192, 0, torch.float16, 256 * 1024, False)
+        va.init_kvcache(2, 2, 64, 2, 8192, 0, torch.float16, 3 * MB, False)
+    with pytest.raises(RuntimeError, match="must divide the device VMM granularity"):
+        va.init_kvcache(2, 2, 64, 2, 8192, 0, torch.float16, 384 * 1024, False)
+    with pytest.raises(RuntimeError, match="never spans two requests"):   # per_req = 1 MiB
+        va.init_kvcache(2, 2, 64, 2, 4096, 0, torch.float16, 256 * 1024, False)
     with pytest.raises(RuntimeError, match="multiple of page_size"):
         va.init_kvcache(2, 2, 64, 2, 1000, 0, torch.float16, 2 * MB, False)
     with pytest.raises(RuntimeError, match="max_batch_size"):
@@ -153,8 +157,58 @@ def random_trace(seed, B, ctx, tpp, steps):
 @pytest.mark.parametrize("mode", ["async", "sync", "async_nodefer"])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_traces_match_oracle(mock_backend, mega, mode, seed):
+    replay_random_trace(mega, mode, seed, 2 * MB, 12 if mega else 90)
+
+
+def check_chunk_invariants():
+    """Logical (sub-granularity) pages: every live logical page lies inside a mapped 2 MiB chunk,
+    no chunk is mapped without a live page inside, all driver traffic is chunk sized."""
+    cfg, st, log = va.get_config(), va.get_state(), va.get_driver_log()
+    gran, page, per_req = 2 * MB, cfg["page_size"], cfg["virt_buff_size_per_req"]
+    reserves = [r for r in log if r[0] == 1]
+    nt = len(reserves) // 2
+    live = set()
+    for r in log:
+        if r[0] == 3:
+            assert r[2] == gran and r[1] % gran == 0 and r[1] not in live
+            live.add(r[1])
+        elif r[0] == 5:
+            assert r[2] == gran
+            live.remove(r[1])
+    want = set()
+    for req, off, layer, _, _ in st["pagemap"]:
+        assert off // per_req == req
+        for t in (reserves[layer][1], reserves[nt + layer][1]):
+            want.add((t + off) // gran * gran)
+    assert live == want
+    granted = {r[1] for r in log if r[0] == 4}
+    assert live <= granted
+
+
+@pytest.mark.parametrize("page_kb", [64, 256, 1024])
+@pytest.mark.parametrize("mode", ["async", "sync"])
+def test_logical_pages_match_oracle(mock_backend, page_kb, mode):
+    """64 KB ... 1 MB pages (the reference's UVM modes, utils.h:83-86): the bookkeeping is the
+    reference's, physical memory moves in 2 MiB chunks."""
+    page = page_kb * 1024
+    replay_random_trace(False, mode, 3, page, 90 * (2 * MB // page), after_step=check_chunk_invariants)
+    for i in range(6):
+        va.free_batch_idx(i)
+    va.step([0] * 6, True)
+    check_chunk_invariants()
+    assert not va.get_state()["pagemap"]
+
+
+def test_logical_pages_megacache_and_common(mock_backend):
+    page = 256 * 1024
+    replay_random_trace(True, "async", 5, page, 12 * 8, after_step=check_chunk_invariants)
+    with pytest.raises(RuntimeError, match="map_common_pages is not available"):
+        va.map_common_pages(100)
+
+
+def replay_random_trace(mega, mode, seed, page, mem_pages, after_step=None):
     L, Hkv, D, B, ctx = 3, 2, 64, 6, 32768
-    model, _ = make_pair(L, Hkv, D, B, ctx, mega=mega, mem_pages=(12 if mega else 90))
+    model, _ = make_pair(L, Hkv, D, B, ctx, mega=mega, mem_pages=mem_pages, page=page)
     if mode == "async_nodefer":
         va.set_deferred_reclamation(False)
         model.set_deferred_reclamation(False)
@@ -199,6 +253,9 @@ def test_random_traces_match_oracle(mock_backend, mega, mode, seed):
                     va.free_batch_idx(big)
                     model.free_batch_idx(big)
                 assert_same(model)
+                if after_step:
+                    va.wait_background()
+                    after_step()
         assert_same(model)
 
 

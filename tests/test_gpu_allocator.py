@@ -120,13 +120,14 @@ def test_traces_match_live_reference(name):
     T.compare_snaps(mb.snaps, ref_snaps, f"oracle vs LIVE reference [{name}]")
 
 
-@pytest.mark.parametrize("mega", [False, True])
-def test_decode_attention_over_virtual_tensors(mega):
+@pytest.mark.parametrize("mega,page", [(False, 2 * MB), (True, 2 * MB), (False, 256 * 1024)])
+def test_decode_attention_over_virtual_tensors(mega, page):
     """The fa_vattn flow end to end: allocator -> cache_flat prefill write -> decode with append,
-    reading the virtual tensors with cache_batch_idx (wrapper.py:151-155,194-205)."""
+    reading the virtual tensors with cache_batch_idx (wrapper.py:151-155,194-205).  The 256 KB case
+    is the reference's fi_vattn_256kb page size: logical pages over 2 MiB physical chunks."""
     L, Hkv, D, Hq, B, ctx = 2, 4, 128, 16, 6, 16384
     dtype = torch.bfloat16
-    ts = va.init_kvcache(L, Hkv, D, B, ctx, 0, dtype, 2 * MB, mega)
+    ts = va.init_kvcache(L, Hkv, D, B, ctx, 0, dtype, page, mega)
     va.reserve_physical_pages(256 * MB)
     if mega:
         caches = [(ts[0][:, :, i], ts[1][:, :, i]) for i in range(L)]

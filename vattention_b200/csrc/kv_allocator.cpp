@@ -81,12 +81,20 @@ std::vector<u64> KvAllocator::init_kvcache(u64 num_layers, u64 num_kv_heads, u64
   // vattention.cu:38-47 (do_cuda_init -> granularity).  The reference asserts
   // granularity == page_size (cudaInternal.h:33); any multiple is mappable.
   c.granularity = drv_->init(device);
-  if (page_size % c.granularity != 0)
+  if (page_size < c.granularity) {
+    // the reference's UVM modes (utils.h:83-86, uvmInternal.h:219-226): 64/128/256 KB pages need its
+    // patched nvidia-uvm driver.  Here they are a logical unit: bookkeeping (tokens_per_page, pool,
+    // num_free_kvblocks) follows the reference formulas exactly, physical memory is mapped in
+    // granularity-sized chunks
+    if (c.granularity % page_size != 0)
+      throw InvalidError("[vattn] page_size " + std::to_string(page_size) +
+                         " must divide the device VMM granularity " + std::to_string(c.granularity));
+    c.phys_group = c.granularity / page_size;
+  } else if (page_size % c.granularity != 0) {
     throw InvalidError("[vattn] page_size " + std::to_string(page_size) +
                        " is not a multiple of the device VMM granularity " +
-                       std::to_string(c.granularity) +
-                       " (sub-granularity pages need the reference's patched UVM driver, "
-                       "uvmInternal.h; not available on B200)");
+                       std::to_string(c.granularity));
+  }
 
   // vattention.cu:41-44, 53-56
   c.per_token = num_kv_heads * head_size * bytes_per_elem * (megacache ? num_layers : 1);
@@ -104,12 +112,17 @@ std::vector<u64> KvAllocator::init_kvcache(u64 num_layers, u64 num_kv_heads, u64
   // page*B; we also reject the cases its rounding lets through silently.
   if (raw % page_size != 0)
     throw InvalidError("size_bytes is not a multiple of page_size * shape[0]");
+  if (c.phys_group > 1 && c.per_req % c.granularity != 0)
+    throw InvalidError("[vattn] logical pages: per-request bytes (" + std::to_string(c.per_req) +
+                       ") must be a multiple of the device VMM granularity so that a physical chunk "
+                       "never spans two requests");
 
   u64 nt = megacache ? 1 : num_layers;
   std::vector<u64> k(nt), v(nt);
   // vattention.cu:163-186: K tensors are reserved first, then V.
-  for (u64 i = 0; i < nt; i++) k[i] = drv_->reserve(c.virt_size, page_size);
-  for (u64 i = 0; i < nt; i++) v[i] = drv_->reserve(c.virt_size, page_size);
+  const u64 align = page_size < c.granularity ? c.granularity : page_size;
+  for (u64 i = 0; i < nt; i++) k[i] = drv_->reserve(c.virt_size, align);
+  for (u64 i = 0; i < nt; i++) v[i] = drv_->reserve(c.virt_size, align);
 
   cfg_ = c;
   k_ptr_ = k;
@@ -118,6 +131,7 @@ std::vector<u64> KvAllocator::init_kvcache(u64 num_layers, u64 num_kv_heads, u64
   seq_lens_.assign(max_batch_size, 0);
   pagemap_.clear();
   shared_refs_.clear();
+  chunks_.clear();
   configured_ = true;
   log("Initialized CUDA context and memory config etc...");
   log("num_tokens_per_kvblock: " + std::to_string(c.tokens_per_page));
@@ -137,11 +151,21 @@ u64 KvAllocator::reserve_physical_pages(u64 free_memory) {
   u64 n = free_memory / cfg_.page_size;
   n -= n % (2 * cfg_.num_layers);
   log("Reserving " + std::to_string(n) + " pages of size " + std::to_string(cfg_.page_size) + " ...");
+  const u64 before = pool_.size();
   while (pool_.size() < n) {
     PhysPage p;
-    p.handle = drv_->create(cfg_.page_size);
+    p.handle = logical() ? 0 : drv_->create(cfg_.page_size);
     p.id = created_++;
     pool_.push_back(p);
+  }
+  if (logical() && pool_.size() > before) {
+    // chunks for the new logical bytes, plus one per (request, tensor) for internal fragmentation
+    // (a request's last chunk in a tensor may hold fewer than phys_group pages)
+    const u64 tensors = 2 * (cfg_.megacache ? 1 : cfg_.num_layers);
+    u64 want = (pool_.size() * cfg_.page_size + cfg_.granularity - 1) / cfg_.granularity +
+               cfg_.max_batch_size * tensors;
+    u64 have = chunk_pool_.size() + chunks_.size();
+    for (; have < want; have++) chunk_pool_.push_back(drv_->create(cfg_.granularity));
   }
   return pool_.size();
 }
@@ -170,9 +194,39 @@ PhysPage KvAllocator::pop_page() {
 
 void KvAllocator::map_pair(u64 req, u64 layer, u64 off, PhysPage k, PhysPage v) {
   // cudaInternal.h:70-82 minus the per-page cuMemSetAccess (batched by callers)
-  drv_->map(k_ptr_[layer] + off, cfg_.page_size, k.handle);
-  drv_->map(v_ptr_[layer] + off, cfg_.page_size, v.handle);
+  if (logical()) {
+    chunk_ref(k_ptr_[layer], off);
+    chunk_ref(v_ptr_[layer], off);
+  } else {
+    drv_->map(k_ptr_[layer] + off, cfg_.page_size, k.handle);
+    drv_->map(v_ptr_[layer] + off, cfg_.page_size, v.handle);
+  }
   pagemap_[Key(req, off, layer)] = std::make_pair(k, v);
+}
+
+void KvAllocator::chunk_ref(u64 base, u64 off) {
+  const u64 va = base + off / cfg_.granularity * cfg_.granularity;
+  auto it = chunks_.find(va);
+  if (it != chunks_.end()) {
+    it->second.second++;
+    return;
+  }
+  if (chunk_pool_.empty()) throw OomError("***** page pool is empty *****");
+  const u64 h = chunk_pool_.back();
+  chunk_pool_.pop_back();
+  drv_->map(va, cfg_.granularity, h);
+  drv_->set_access(va, cfg_.granularity);
+  chunks_[va] = std::make_pair(h, (u64)1);
+}
+
+void KvAllocator::chunk_unref(u64 base, u64 off) {
+  const u64 va = base + off / cfg_.granularity * cfg_.granularity;
+  auto it = chunks_.find(va);
+  if (it == chunks_.end()) throw StateError("[vattn] physical chunk missing on unmap");
+  if (--it->second.second > 0) return;
+  drv_->unmap(va, cfg_.granularity);
+  chunk_pool_.push_back(it->second.first);
+  chunks_.erase(it);
 }
 
 void KvAllocator::grow(u64 req, u64 nblocks, bool sync, u64* pages_counter) {
@@ -202,7 +256,7 @@ void KvAllocator::grow(u64 req, u64 nblocks, bool sync, u64* pages_counter) {
     done++;
   }
   if (done) {
-    for (u64 layer = 0; layer < nl; layer++) {
+    for (u64 layer = 0; layer < nl && !logical(); layer++) {  // (logical mode grants access per chunk)
       drv_->set_access(k_ptr_[layer] + first_off, done * cfg_.page_size);
       drv_->set_access(v_ptr_[layer] + first_off, done * cfg_.page_size);
     }
@@ -219,8 +273,13 @@ void KvAllocator::unmap_one(u64 req) {
   for (u64 layer = 0; layer < nl; layer++) {
     auto it = pagemap_.find(Key(req, off, layer));
     if (it == pagemap_.end()) throw StateError("[vattn] page map entry missing on unmap");
-    drv_->unmap(k_ptr_[layer] + off, cfg_.page_size);
-    drv_->unmap(v_ptr_[layer] + off, cfg_.page_size);
+    if (logical()) {
+      chunk_unref(k_ptr_[layer], off);
+      chunk_unref(v_ptr_[layer], off);
+    } else {
+      drv_->unmap(k_ptr_[layer] + off, cfg_.page_size);
+      drv_->unmap(v_ptr_[layer] + off, cfg_.page_size);
+    }
     PhysPage pg[2] = {it->second.first, it->second.second};  // K pushed first, then V
     for (const PhysPage& p : pg) {
       auto sh = shared_refs_.find(p.id);
@@ -429,6 +488,7 @@ void KvAllocator::map_common_pages(u64 num_tokens) {
   wait_idle(lk);
   require_configured();
   // vattention.cu:326-373 + mux.h:68-85
+  if (logical()) throw InvalidError("[vattn] map_common_pages is not available with logical (sub-granularity) pages");
   u64 nblocks = tokens_to_pages(num_tokens);
   if (nblocks == 0) return;
   if (!kvblocks_available(nblocks)) {
@@ -469,7 +529,11 @@ void KvAllocator::cleanup() {
     drv_->addr_free(k_ptr_[i], cfg_.virt_size);
     drv_->addr_free(v_ptr_[i], cfg_.virt_size);
   }
-  for (const PhysPage& p : pool_) drv_->release(p.handle);
+  for (const PhysPage& p : pool_)
+    if (!logical()) drv_->release(p.handle);
+  for (u64 h : chunk_pool_) drv_->release(h);
+  chunk_pool_.clear();
+  chunks_.clear();
   pool_.clear();
   pagemap_.clear();
   shared_refs_.clear();

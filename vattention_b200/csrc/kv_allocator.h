@@ -49,6 +49,10 @@ struct KvConfig {
   int device = 0;
   u64 tokens_per_page = 0, per_token = 0, per_req = 0, virt_size = 0;
   u64 max_pages_per_req = 0, granularity = 0;
+  // page_size < granularity: pages are a LOGICAL bookkeeping unit (the reference's 64/128/256 KB UVM
+  // modes); physical memory is mapped in granularity-sized chunks, each backing `phys_group`
+  // consecutive logical pages of one request in one tensor
+  u64 phys_group = 1;
 };
 
 struct StepStats {
@@ -101,6 +105,9 @@ class KvAllocator {
   u64 overcommitted() const;
   PhysPage pop_page();
   void map_pair(u64 req, u64 layer, u64 off, PhysPage k, PhysPage v);
+  bool logical() const { return cfg_.phys_group > 1; }
+  void chunk_ref(u64 tensor_base, u64 off);    // logical mode: back the chunk holding `off`
+  void chunk_unref(u64 tensor_base, u64 off);  // ... and drop it when its last page goes
   void grow(u64 req, u64 nblocks, bool sync, u64* pages_counter);
   void unmap_one(u64 req);
   void release_some(u64 req, u64 retain);
@@ -128,6 +135,9 @@ class KvAllocator {
   u64 created_ = 0;
   std::map<Key, std::pair<PhysPage, PhysPage>> pagemap_;
   std::unordered_map<u64, u64> shared_refs_;  // page id -> live mappings (map_common_pages)
+  // logical mode: physical chunk pool and, per chunk VA, (handle, number of logical pages inside)
+  std::vector<u64> chunk_pool_;
+  std::unordered_map<u64, std::pair<u64, u64>> chunks_;
   std::vector<u64> mapped_pages_, seq_lens_;
 
   void* compute_stream_ = nullptr;
