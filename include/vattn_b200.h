@@ -207,6 +207,13 @@ typedef struct {
    * May be NULL when that returns 0.                                        */
   void* workspace;
   size_t workspace_bytes;
+  /* Rotary embedding applied to q and k_new before the append (flash_api.cpp:1298-1310,1503-1527;
+   * flash_fwd_kernel.h:684-830).  cos/sin: [seqlen_ro, rotary_dim/2] contiguous, dtype of q;
+   * NULL = none.  Requires k_new; rotary_dim % 16 == 0, <= head_dim; seqlen_ro >= seqlen_k.
+   * rotary_interleaved: 1 pairs dims (2j, 2j+1), 0 pairs (j, j + rotary_dim/2).             */
+  const void* rotary_cos;
+  const void* rotary_sin;
+  int32_t rotary_dim, rotary_interleaved, seqlen_ro;
 } vattn_fwd_params_t;
 
 size_t vattn_fwd_kvcache_workspace(const vattn_fwd_params_t* p);

@@ -42,12 +42,34 @@ def cache_flat_ref(key: torch.Tensor, value: torch.Tensor, k_cache: torch.Tensor
     v_cache[:n].copy_(value)
 
 
+def rotary_ref(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, positions: torch.Tensor,
+               interleaved: bool) -> torch.Tensor:
+    """x [S, H, D] rotated at `positions` [S] (rotary.h / flash_fwd_kernel.h:684-830):
+    interleaved pairs dims (2j, 2j+1), otherwise (j, j + rotary_dim/2); dims >= rotary_dim pass
+    through; x0' = x0 cos - x1 sin, x1' = x0 sin + x1 cos in fp32, rounded once to x.dtype."""
+    rd = 2 * cos.shape[1]
+    c = cos[positions.long()].float().unsqueeze(1)          # [S, 1, rd/2]
+    s = sin[positions.long()].float().unsqueeze(1)
+    xf = x.float()
+    out = xf.clone()
+    if interleaved:
+        x0, x1 = xf[..., 0:rd:2], xf[..., 1:rd:2]
+        out[..., 0:rd:2] = x0 * c - x1 * s
+        out[..., 1:rd:2] = x0 * s + x1 * c
+    else:
+        x0, x1 = xf[..., :rd // 2], xf[..., rd // 2:rd]
+        out[..., :rd // 2] = x0 * c - x1 * s
+        out[..., rd // 2:rd] = x0 * s + x1 * c
+    return out.to(x.dtype)
+
+
 def attn_with_kvcache_ref(
     q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
     k: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None,
     cache_seqlens: Optional[torch.Tensor] = None, cache_batch_idx: Optional[torch.Tensor] = None,
     softmax_scale: Optional[float] = None, causal: bool = False, update_cache: bool = True,
-    return_lse: bool = False,
+    return_lse: bool = False, rotary_cos: Optional[torch.Tensor] = None,
+    rotary_sin: Optional[torch.Tensor] = None, rotary_interleaved: bool = True,
 ):
     """flash_attn_with_kvcache on CPU in fp32.  q [B,Sq,Hq,D]; caches [Bc,Sk,Hkv,D] (updated in
     place when k/v are given and update_cache); returns out [B,Sq,Hq,D] in q.dtype."""
@@ -60,12 +82,20 @@ def attn_with_kvcache_ref(
     for b in range(B):
         slot = int(cache_batch_idx[b]) if cache_batch_idx is not None else b
         L0 = int(cache_seqlens[b]) if cache_seqlens is not None else Sk
+        qb = q[b]
         if k is not None:
             n_new = k.shape[1]
+            kb = k[b]
+            if rotary_cos is not None:
+                # flash_fwd_kernel.h:693-760 (new keys at L0 + t), :796-804 (queries at L0 + i when
+                # causal, all at L0 otherwise)
+                kb = rotary_ref(kb, rotary_cos, rotary_sin, L0 + torch.arange(n_new), rotary_interleaved)
+                qpos = L0 + (torch.arange(Sq) if causal else torch.zeros(Sq, dtype=torch.long))
+                qb = rotary_ref(qb, rotary_cos, rotary_sin, qpos, rotary_interleaved)
             if update_cache:
-                k_cache[slot, L0:L0 + n_new] = k[b]       # flash_fwd_kernel.h:685-790
+                k_cache[slot, L0:L0 + n_new] = kb         # flash_fwd_kernel.h:685-790
                 v_cache[slot, L0:L0 + n_new] = v[b]
-            kk = torch.cat([k_cache[slot, :L0], k[b]], dim=0).float()
+            kk = torch.cat([k_cache[slot, :L0], kb], dim=0).float()
             vv = torch.cat([v_cache[slot, :L0], v[b]], dim=0).float()
             Lk = L0 + n_new                                # block_info.h:37-41
         else:
@@ -74,7 +104,7 @@ def attn_with_kvcache_ref(
             vv = v_cache[slot, :Lk].float()
         if Lk == 0:
             continue
-        qq = q[b].float()                                  # [Sq, Hq, D]
+        qq = qb.float()                                    # [Sq, Hq, D]
         # GQA: q head h reads kv head h // g
         kk = kk.repeat_interleave(g, dim=1)                # [Lk, Hq, D]
         vv = vv.repeat_interleave(g, dim=1)

@@ -19,7 +19,14 @@ CASES = [
     ("prefill_chunk_bf16", 1, 48, 8, 2, 128, 176, torch.bfloat16, False, True, 1),
     ("prefill_square_fp16", 2, 40, 4, 2, 128, 40, torch.float16, False, True, 2),
     ("prefill_masked_rows_fp16", 1, 24, 4, 4, 64, 64, torch.float16, False, True, 1),
+    # rotary cases (name prefix rope_): (interleaved, rotary_dim) in ROPE below
+    ("rope_decode_neox_bf16", 3, 1, 8, 2, 128, 160, torch.bfloat16, True, True, 4),
+    ("rope_decode_gptj_fp16", 2, 1, 4, 4, 128, 96, torch.float16, True, True, 2),
+    ("rope_append4_causal_partial_fp16", 2, 4, 4, 2, 128, 80, torch.float16, True, True, 3),
+    ("rope_append4_noncausal_bf16", 2, 4, 4, 2, 64, 80, torch.bfloat16, True, False, 2),
 ]
+ROPE = {"rope_decode_neox_bf16": (False, 128), "rope_decode_gptj_fp16": (True, 128),
+        "rope_append4_causal_partial_fp16": (False, 64), "rope_append4_noncausal_bf16": (True, 32)}
 
 
 def main(outdir):
@@ -44,12 +51,21 @@ def main(outdir):
         idx = torch.randperm(slots, generator=g)[:B].int() if slots != B else None
         dev = lambda t: None if t is None else t.cuda()
         kc_d, vc_d = dev(kc), dev(vc)
-        out = flash_attn_with_kvcache(dev(q), kc_d, vc_d, dev(kn), dev(vn), cache_seqlens=dev(lens),
-                                      cache_batch_idx=dev(idx), causal=causal)
+        cos = sin = None
+        interleaved = True
+        if name in ROPE:
+            interleaved, rd = ROPE[name]
+            ang = torch.rand(Sk, rd // 2, generator=g) * 6.283
+            cos, sin = torch.cos(ang).to(dtype), torch.sin(ang).to(dtype)
+        out = flash_attn_with_kvcache(dev(q), kc_d, vc_d, dev(kn), dev(vn), rotary_cos=dev(cos),
+                                      rotary_sin=dev(sin), cache_seqlens=dev(lens),
+                                      cache_batch_idx=dev(idx), causal=causal,
+                                      rotary_interleaved=interleaved)
         torch.cuda.synchronize()
         torch.save({"name": name, "source": f"flash_attn {flash_attn.__version__} on {torch.cuda.get_device_name(0)}",
                     "q": q, "k_cache": kc, "v_cache": vc, "k": kn, "v": vn, "cache_seqlens": lens,
                     "cache_batch_idx": idx, "causal": causal, "out": out.cpu(),
+                    "rotary_cos": cos, "rotary_sin": sin, "rotary_interleaved": interleaved,
                     "k_cache_after": kc_d.cpu(), "v_cache_after": vc_d.cpu()},
                    os.path.join(outdir, f"attn_{name}.pt"))
         print(name, tuple(out.shape))

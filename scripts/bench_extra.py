@@ -6,6 +6,8 @@ DESIGN.md / profiles/ quote for the other rows of SURVEY 8(d).  One JSON line pe
   python scripts/bench_extra.py prefill [--chunk 2048] [--impl ours|fa|fi]   configs[2]
   python scripts/bench_extra.py pod [--impl ours|fa]                         configs[3]
   python scripts/bench_extra.py alloc                                        step_async overlap
+  python scripts/bench_extra.py decode [--ragged] [--dtype fp16] [--hq 8 --hkv 1 --batch 16 --ctx 131072]
+                                                                             configs[1] variants, config 5 per-GPU shapes
 """
 from __future__ import annotations
 
@@ -53,7 +55,7 @@ def prefill(args):
     Hq, Hkv, D, S, c = 32, 4, 128, args.ctx, args.chunk
     dtype = torch.bfloat16
     torch.zeros(1, device=DEV)
-    kc, vc = va.init_kvcache(1, Hkv, D, 1, S, 0, dtype, PAGE, False)
+    kc, vc = va.init_kvcache(1, Hkv, D, 1, S, 0, dtype, args.page_kb << 10, False)
     va.reserve_physical_pages(2 * S * Hkv * D * 2 + (8 << 20))
     va.step([S], True)
     g = torch.Generator(device=DEV).manual_seed(0)
@@ -83,7 +85,7 @@ def prefill(args):
     flops = sum(4 * Hq * D * (c * p + c * (c + 1) // 2) for p in range(0, S, c))
     _, burst, sustained = peaks()
     tf = flops / (ms * 1e-3) / 1e12
-    out = {"workload": f"prefill ctx{S} chunk{c} Yi-6B shapes bf16", "impl": args.impl,
+    out = {"workload": f"prefill ctx{S} chunk{c} Yi-6B shapes bf16, page {args.page_kb} KB", "impl": args.impl,
            "ms_per_prefill": round(ms, 2), "tflops": round(tf, 1), "flops": flops,
            "frac_of_measured_bf16_burst": round(tf / burst, 4),
            "frac_of_measured_bf16_sustained": round(tf / sustained, 4)}
@@ -99,10 +101,11 @@ def pod(args):
     """configs[3]: Llama-3-8B shapes fp16, 8 prefills (16K queries over 16K keys) + 56 decodes at 4K
     context, one layer.  fused call vs the two calls back to back."""
     Hq, Hkv, D = 32, 8, 128
-    Bp, Sp, Bd, Sd = args.prefills, args.prefill_len, 56, 4096
+    Bp, Sp, Bd, Sd = args.prefills, args.prefill_len, args.decodes, args.decode_len
     dtype = torch.float16
     g = torch.Generator(device=DEV).manual_seed(0)
-    q_p = torch.randn(Bp, Sp, Hq, D, device=DEV, generator=g).to(dtype)
+    Sq = args.prefill_chunk or Sp       # wrapper-realistic variant: one chunk deep in a long context
+    q_p = torch.randn(Bp, Sq, Hq, D, device=DEV, generator=g).to(dtype)
     kc_p = torch.randn(Bp, Sp, Hkv, D, device=DEV, generator=g).to(dtype)
     vc_p = torch.randn(Bp, Sp, Hkv, D, device=DEV, generator=g).to(dtype)
     lens_p = torch.full((Bp,), Sp, dtype=torch.int32, device=DEV)
@@ -133,11 +136,22 @@ def pod(args):
                                          cache_seqlens_p=lens_p, cache_seqlens_d=lens_d,
                                          cache_batch_idx=idx, fused_params=15)
 
+    side = torch.cuda.Stream(device=DEV)
+
+    def run_two_streams():              # attn_sweep.py:63-65's third arm
+        side.wait_stream(torch.cuda.current_stream(DEV))
+        with torch.cuda.stream(side):
+            run_d()
+        run_p()
+        torch.cuda.current_stream(DEV).wait_stream(side)
+
     t_p, t_d = timed(run_p, 1, args.iters), timed(run_d, 3, 20)
     t_s = timed(run_serial, 1, args.iters)
-    out = {"workload": f"pod {Bp}x prefill@{Sp} + {Bd}x decode@{Sd} Llama-3-8B fp16", "impl": args.impl,
-           "prefill_ms": round(t_p, 3), "decode_ms": round(t_d, 4), "serial_ms": round(t_s, 3)}
-    flops = Bp * 4 * Hq * D * (Sp * (Sp + 1) // 2)
+    t_2 = timed(run_two_streams, 1, args.iters)
+    out = {"workload": f"pod {Bp}x prefill {Sq}q@{Sp} + {Bd}x decode@{Sd} Llama-3-8B fp16", "impl": args.impl,
+           "prefill_ms": round(t_p, 3), "decode_ms": round(t_d, 4), "serial_ms": round(t_s, 3),
+           "two_streams_ms": round(t_2, 3)}
+    flops = Bp * 4 * Hq * D * (Sq * (Sp - Sq) + Sq * (Sq + 1) // 2)
     dbytes = 2 * 2 * Hkv * D * Bd * Sd
     hbm, burst, _ = peaks()
     out["prefill_tflops"] = round(flops / (t_p * 1e-3) / 1e12, 1)
@@ -203,9 +217,64 @@ def alloc(args):
                                   f"{args.alloc_steps} steps", **res}))
 
 
+def decode(args):
+    """configs[1] variants and config 5's per-GPU shapes: ONE layer-call of decode attention with the
+    fused k/v append over vAttention tensors (num_layers = 1, as bench_pagesize.py does).  Bytes =
+    SURVEY 8(d): K and V once (+1 appended row), Q read, O write, k/v new write."""
+    Hq, Hkv, D, B, ctx = args.hq, args.hkv, 128, args.batch, args.ctx
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype]
+    torch.zeros(1, device=DEV)
+    kc, vc = va.init_kvcache(1, Hkv, D, B, ctx, 0, dtype, PAGE, False)
+    va.reserve_physical_pages(2 * B * ctx * Hkv * D * 2 + (8 << 20))
+    g = torch.Generator().manual_seed(0)
+    if args.ragged:
+        lens = torch.randint(ctx // 2, ctx, (B,), generator=g).tolist()
+    else:
+        lens = [ctx - 1] * B
+    va.step([n + 1 for n in lens], True)
+    gd = torch.Generator(device=DEV).manual_seed(0)
+    for b in range(B):
+        kc[b, :lens[b]].normal_(generator=gd)
+        vc[b, :lens[b]].normal_(generator=gd)
+    q = torch.randn(B, 1, Hq, D, device=DEV, generator=gd).to(dtype)
+    kn = torch.randn(B, 1, Hkv, D, device=DEV, generator=gd).to(dtype)
+    vn = torch.randn(B, 1, Hkv, D, device=DEV, generator=gd).to(dtype)
+    sl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    idx = torch.arange(B, device=DEV).int()
+    mx = max(lens) + 1
+    if args.impl == "fa":
+        from flash_attn import flash_attn_with_kvcache as fwd
+    else:
+        fwd = att.flash_attn_with_kvcache
+    # every layer-call reads 2*B*ctx*Hkv*D*2 bytes; below the 126 MB L2 rotate over nothing would be
+    # wrong, so small shapes are flushed by a 256 MB write between calls (outside the events)
+    kv_bytes = 2 * 2 * Hkv * D * sum(n + 1 for n in lens)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV) if kv_bytes < (512 << 20) else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.calls)]
+    for i in range(3 + args.calls):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        if i >= 3:
+            ev[i - 3][0].record()
+        fwd(q, kc[:, :mx], vc[:, :mx], kn, vn, cache_seqlens=sl, cache_batch_idx=idx, causal=True)
+        if i >= 3:
+            ev[i - 3][1].record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2]
+    nbytes = kv_bytes + 2 * 2 * B * Hq * D + 2 * 2 * B * Hkv * D
+    hbm, _, _ = peaks()
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"workload": f"decode B{B} Hq{Hq} Hkv{Hkv} D128 ctx{ctx}{' ragged U[ctx/2,ctx)' if args.ragged else ''} "
+                                  f"{args.dtype}, 1 layer-call incl. append", "impl": args.impl,
+                      "ms_per_layer_call_median": round(ms, 4), "bytes": nbytes, "gbps": round(gbs, 1),
+                      "frac_of_measured_copy_peak": round(gbs / hbm, 4), "frac_of_8TBps": round(gbs / 8000, 4),
+                      "l2_flush_between_calls": flush is not None}))
+    va.cleanup()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["prefill", "pod", "alloc"])
+    ap.add_argument("what", choices=["prefill", "pod", "alloc", "decode"])
     ap.add_argument("--impl", default="ours", choices=["ours", "fa", "fi"])
     ap.add_argument("--chunk", type=int, default=2048)
     ap.add_argument("--ctx", type=int, default=131072)
@@ -213,5 +282,15 @@ if __name__ == "__main__":
     ap.add_argument("--prefills", type=int, default=8)
     ap.add_argument("--prefill-len", type=int, default=16384)
     ap.add_argument("--alloc-steps", type=int, default=48)
+    ap.add_argument("--page-kb", type=int, default=2048)
+    ap.add_argument("--prefill-chunk", type=int, default=0)
+    ap.add_argument("--decodes", type=int, default=56)
+    ap.add_argument("--decode-len", type=int, default=4096)
+    ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--hq", type=int, default=32)
+    ap.add_argument("--hkv", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--calls", type=int, default=20)
     a = ap.parse_args()
-    {"prefill": prefill, "pod": pod, "alloc": alloc}[a.what](a)
+    {"prefill": prefill, "pod": pod, "alloc": alloc, "decode": decode}[a.what](a)

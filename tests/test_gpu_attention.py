@@ -390,3 +390,65 @@ def test_wide_pitch_views_take_the_tensor_core_path(dtype):
         want = ref.attn_with_kvcache_ref(qp, kref, vref, cache_seqlens=lens_p, causal=True)
         out = att.flash_attn_with_kvcache(qp.to(DEV), kc, vc, cache_seqlens=lens_p.to(DEV), causal=True, impl="tc")
         close(out, want, dtype)
+
+
+# ---- rotary embedding fused with the append (flash_api.cpp:1503-1527) -------------
+
+def rope_tables(Sk, rd, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    ang = torch.rand(Sk, rd // 2, generator=g) * 6.283
+    return torch.cos(ang).to(dtype), torch.sin(ang).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("B,Sq,Hq,Hkv,D,Sk,rd,interleaved,causal", [
+    (5, 1, 32, 8, 128, 1500, 128, False, True),    # decode, GQA 4 (tensor-core path), NeoX full dim
+    (3, 1, 8, 8, 128, 700, 64, True, True),        # decode MHA, GPT-J, partial rotary
+    (2, 200, 8, 2, 128, 640, 128, False, True),    # chunk append, causal: query i at L0 + i
+    (2, 6, 4, 2, 64, 96, 32, True, False),         # non-causal: every query at L0
+])
+def test_rotary_append_matches_oracle(dtype, impl, B, Sq, Hq, Hkv, D, Sk, rd, interleaved, causal):
+    q, kc, vc, kn, vn, lens, idx = make_case(B, Sq, Hq, Hkv, D, Sk, dtype, seed=11)
+    cos, sin = rope_tables(Sk, rd, dtype, 5)
+    kc_ref, vc_ref = kc.clone(), vc.clone()
+    want = ref.attn_with_kvcache_ref(q, kc_ref, vc_ref, kn, vn, lens, idx, None, causal,
+                                     rotary_cos=cos, rotary_sin=sin, rotary_interleaved=interleaved)
+    d = lambda t: None if t is None else t.to(DEV)
+    kc_d, vc_d, q_d, kn_d = d(kc), d(vc), d(q), d(kn)
+    out = att.flash_attn_with_kvcache(q_d, kc_d, vc_d, kn_d, d(vn), rotary_cos=d(cos), rotary_sin=d(sin),
+                                      cache_seqlens=d(lens), cache_batch_idx=d(idx), causal=causal,
+                                      rotary_interleaved=interleaved, impl=impl)
+    torch.cuda.synchronize()
+    close(out, want, dtype)
+    # the cache holds the ROTATED keys (one rounding; an fma contraction may move a tie by one ulp),
+    # values verbatim; the caller's q and k are left untouched
+    ulp = {torch.bfloat16: 2.0 ** -7, torch.float16: 2.0 ** -10}[dtype]
+    got_k, want_k = kc_d.float().cpu(), kc_ref.float()
+    assert torch.all((got_k - want_k).abs() <= ulp * want_k.abs() + 1e-6)
+    assert (got_k != want_k).float().mean() < 0.01
+    assert torch.equal(vc_d.cpu(), vc_ref)
+    assert torch.equal(q_d.cpu(), q) and torch.equal(kn_d.cpu(), kn)
+
+
+def test_rotary_argument_rules():
+    q, kc, vc, kn, vn, lens, idx = make_case(2, 1, 4, 2, 128, 64, torch.float16)
+    cos, sin = rope_tables(64, 64, torch.float16, 0)
+    d = lambda t: None if t is None else t.to(DEV)
+    with pytest.raises(RuntimeError, match="new key / value to be appended to KV cache must also be provided"):
+        att.flash_attn_with_kvcache(d(q), d(kc), d(vc), rotary_cos=d(cos), rotary_sin=d(sin),
+                                    cache_seqlens=d(lens), cache_batch_idx=d(idx))
+    with pytest.raises(RuntimeError, match="rotary sin must also be provided"):
+        att.flash_attn_with_kvcache(d(q), d(kc), d(vc), d(kn), d(vn), rotary_cos=d(cos),
+                                    cache_seqlens=d(lens), cache_batch_idx=d(idx))
+    with pytest.raises(RuntimeError, match="same dtype as query"):
+        att.flash_attn_with_kvcache(d(q), d(kc), d(vc), d(kn), d(vn), rotary_cos=d(cos).bfloat16(),
+                                    rotary_sin=d(sin).bfloat16(), cache_seqlens=d(lens), cache_batch_idx=d(idx))
+    c24, s24 = rope_tables(64, 24, torch.float16, 0)
+    with pytest.raises(RuntimeError, match="divisible by 16"):
+        att.flash_attn_with_kvcache(d(q), d(kc), d(vc), d(kn), d(vn), rotary_cos=d(c24), rotary_sin=d(s24),
+                                    cache_seqlens=d(lens), cache_batch_idx=d(idx))
+    short_c, short_s = rope_tables(32, 64, torch.float16, 0)
+    with pytest.raises(RuntimeError, match="at least the seqlen of KV cache"):
+        att.flash_attn_with_kvcache(d(q), d(kc), d(vc), d(kn), d(vn), rotary_cos=d(short_c), rotary_sin=d(short_s),
+                                    cache_seqlens=d(lens), cache_batch_idx=d(idx))

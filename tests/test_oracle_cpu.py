@@ -62,3 +62,38 @@ def test_fully_masked_rows_zero_and_empty_cache():
     assert torch.all(out[0, :3] == 0) and not torch.all(out[0, 3] == 0)
     out = ref.attn_with_kvcache_ref(q, k, k.clone(), cache_seqlens=torch.tensor([0], dtype=torch.int32))
     assert torch.all(out == 0)
+
+
+def test_rotary_restatement_properties():
+    """rotary_ref (flash_fwd_kernel.h:684-830): rotations preserve norms, position 0 of a standard
+    frequency table is the identity, and <R(p) q, R(p') k> depends on p - p' only -- for both pairings;
+    dims beyond rotary_dim pass through; queries of a non-causal call all sit at cache_seqlens."""
+    import torch
+    from oracle.attention_ref import attn_with_kvcache_ref, rotary_ref
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 3, 64, generator=g)
+    inv = 1.0 / (10000 ** (torch.arange(0, 24) / 24))
+    ang = torch.arange(100)[:, None] * inv[None]
+    cos, sin = torch.cos(ang), torch.sin(ang)           # rotary_dim 48 of 64
+    for il in (True, False):
+        y = rotary_ref(x, cos, sin, torch.tensor([0, 3, 7, 50, 99]), il)
+        assert torch.allclose(y.norm(dim=-1), x.norm(dim=-1), atol=1e-4)
+        assert torch.equal(y[0], x[0]) and torch.equal(y[..., 48:], x[..., 48:])
+        q, k = torch.randn(1, 1, 64, generator=g), torch.randn(1, 1, 64, generator=g)
+        a = (rotary_ref(q, cos, sin, torch.tensor([10]), il) * rotary_ref(k, cos, sin, torch.tensor([4]), il)).sum()
+        b = (rotary_ref(q, cos, sin, torch.tensor([56]), il) * rotary_ref(k, cos, sin, torch.tensor([50]), il)).sum()
+        assert abs(a - b) < 1e-3
+    # end to end: rotating by hand then calling without rotary == calling with rotary
+    q = torch.randn(2, 3, 4, 64, generator=g)
+    kc, vc = torch.randn(2, 40, 2, 64, generator=g), torch.randn(2, 40, 2, 64, generator=g)
+    kn, vn = torch.randn(2, 3, 2, 64, generator=g), torch.randn(2, 3, 2, 64, generator=g)
+    lens = torch.tensor([20, 37], dtype=torch.int32)
+    for causal in (True, False):
+        k1, v1, k2, v2 = kc.clone(), vc.clone(), kc.clone(), vc.clone()
+        got = attn_with_kvcache_ref(q, k1, v1, kn, vn, lens, None, None, causal, rotary_cos=cos, rotary_sin=sin,
+                                    rotary_interleaved=False)
+        qr = torch.stack([rotary_ref(q[b], cos, sin, int(lens[b]) + (torch.arange(3) if causal else torch.zeros(3, dtype=torch.long)), False)
+                          for b in range(2)])
+        kr = torch.stack([rotary_ref(kn[b], cos, sin, int(lens[b]) + torch.arange(3), False) for b in range(2)])
+        want = attn_with_kvcache_ref(qr, k2, v2, kr, vn, lens, None, None, causal)
+        assert torch.equal(got, want) and torch.equal(k1, k2) and torch.equal(v1, v2)

@@ -56,6 +56,8 @@ class FwdParams(C.Structure):
         ("softmax_scale", C.c_float),
         ("impl", C.c_int32), ("num_splits", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("rotary_cos", C.c_void_p), ("rotary_sin", C.c_void_p),
+        ("rotary_dim", C.c_int32), ("rotary_interleaved", C.c_int32), ("seqlen_ro", C.c_int32),
     ]
 
 

@@ -33,10 +33,11 @@ _workspace: dict = {}
 def _ws(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
     if nbytes == 0:
         return None
-    buf = _workspace.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)  # calls on two streams may overlap
+    buf = _workspace.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspace[device] = buf
+        _workspace[key] = buf
     return buf
 
 
@@ -52,7 +53,7 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
 
 
 def _fill_params(q, k_cache, v_cache, k, v, out, cache_seqlens, cache_batch_idx,
-                 softmax_scale, causal, impl, num_splits, lse) -> FwdParams:
+                 softmax_scale, causal, impl, num_splits, lse, rotary=None) -> FwdParams:
     p = FwdParams()
     b, sq, hq, d = q.shape
     cb, sk, hkv, dk = k_cache.shape
@@ -80,7 +81,34 @@ def _fill_params(q, k_cache, v_cache, k, v, out, cache_seqlens, cache_batch_idx,
     p.softmax_scale = float(softmax_scale)
     p.impl = _IMPL[impl] if isinstance(impl, str) else int(impl)
     p.num_splits = int(num_splits)
+    if rotary is not None:
+        cos, sin, interleaved = rotary
+        p.rotary_cos, p.rotary_sin = cos.data_ptr(), sin.data_ptr()
+        p.rotary_dim, p.seqlen_ro = 2 * cos.shape[1], cos.shape[0]
+        p.rotary_interleaved = 1 if interleaved else 0
     return p
+
+
+def _check_rotary(q, k, rotary_cos, rotary_sin):
+    """Argument rules of flash_api.cpp:1503-1527, same messages."""
+    if rotary_cos is None:
+        if rotary_sin is not None:
+            raise RuntimeError("If rotary sin is provided, rotary cos must also be provided")
+        return None
+    if k is None:
+        raise RuntimeError("If rotary cos/sin are provided, new key / value to be appended to KV cache "
+                           "must also be provided")
+    if rotary_sin is None:
+        raise RuntimeError("If rotary cos is provided, rotary sin must also be provided")
+    for name, t in (("rotary_cos", rotary_cos), ("rotary_sin", rotary_sin)):
+        _require_cuda(t, name)
+        if t.dim() != 2 or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous [seqlen_ro, rotary_dim / 2]")
+        if t.dtype != q.dtype:
+            raise RuntimeError("rotary_cos must have the same dtype as query")
+    if rotary_sin.shape != rotary_cos.shape:
+        raise RuntimeError("rotary_sin must have the shape of rotary_cos")
+    return rotary_cos, rotary_sin
 
 
 def _prep(q, k_cache, v_cache, k, v, cache_seqlens, cache_batch_idx, softmax_scale):
@@ -131,16 +159,22 @@ def flash_attn_with_kvcache(
     q [B, Sq, Hq, D]; k_cache/v_cache [Bc, Sk, Hkv, D] (any outer strides, e.g. vAttention
     virtual tensors or megacache views); k/v [B, Snew, Hkv, D] are written in place at rows
     cache_seqlens[b].. of slot cache_batch_idx[b] before attending; returns [B, Sq, Hq, D].
-    Options the sarathi wrappers never pass (rotary, block_table, ALiBi, sliding window,
-    softcap, left padding) are rejected rather than ignored.
+    rotary_cos / rotary_sin [seqlen_ro, rotary_dim/2] rotate q and the appended k first (new key t
+    at position cache_seqlens[b]+t; query i at cache_seqlens[b]+i when causal, cache_seqlens[b]
+    otherwise; rotary_interleaved pairs dims (2j,2j+1), else (j, j+rotary_dim/2)).
+    Options the sarathi wrappers never pass (block_table, ALiBi, sliding window, softcap, left
+    padding) are rejected rather than ignored.
     """
     if block_table is not None:
         raise RuntimeError("block_table is not supported: vAttention K/V is contiguous by construction")
-    if rotary_cos is not None or rotary_sin is not None or alibi_slopes is not None \
-            or cache_leftpad is not None or softcap != 0.0 or tuple(window_size) != (-1, -1):
-        raise RuntimeError("rotary / alibi / leftpad / softcap / sliding window are outside the vAttention hot path")
+    if alibi_slopes is not None or cache_leftpad is not None or softcap != 0.0 \
+            or tuple(window_size) != (-1, -1):
+        raise RuntimeError("alibi / leftpad / softcap / sliding window are outside the vAttention hot path")
     cache_seqlens, cache_batch_idx, softmax_scale = _prep(
         q, k_cache, v_cache, k, v, cache_seqlens, cache_batch_idx, softmax_scale)
+    rot = _check_rotary(q, k, rotary_cos, rotary_sin)
+    if rot is not None:
+        rot = (rot[0], rot[1], rotary_interleaved)
     if out is None:
         out = torch.empty_like(q)
     if q.shape[0] == 0:
@@ -149,7 +183,7 @@ def flash_attn_with_kvcache(
     if return_softmax_lse:
         lse = torch.empty((q.shape[0], q.shape[2], q.shape[1]), dtype=torch.float32, device=q.device)
     p = _fill_params(q, k_cache, v_cache, k, v, out, cache_seqlens, cache_batch_idx,
-                     softmax_scale, causal, impl, num_splits, lse)
+                     softmax_scale, causal, impl, num_splits, lse, rot)
     need = lib.vattn_fwd_kvcache_workspace(C.byref(p))
     ws = _ws(q.device, need)
     if ws is not None:

@@ -36,6 +36,10 @@ int run_umma_selftest(char* buf, size_t len, cudaStream_t);
 // fused prefill + decode (attn_pod_tc.cu)
 bool pod_tc_supported(const vattn_fwd_params_t&, const vattn_fwd_params_t&, std::string* why);
 size_t pod_tc_workspace(const vattn_fwd_params_t&, const vattn_fwd_params_t&);
+// rope.cu
+size_t rope_workspace_bytes(const vattn_fwd_params_t&);
+vattn_fwd_params_t rope_rotated_view(const vattn_fwd_params_t&, const void*, const void*);
+vattn_fwd_params_t launch_rope(const vattn_fwd_params_t&, cudaStream_t);
 void launch_pod_tc(const vattn_fwd_params_t&, const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
 
 // ---- per-launch kernel timing -------------------------------------------------------
@@ -104,6 +108,18 @@ void validate(const vattn_fwd_params_t& p) {
     if (p.seqlen_new > p.seqlen_k)
       throw ArgError("If key is supplied, it must have seqlen <= the seqlen of the KV cache");
   }
+  if ((p.rotary_cos == nullptr) != (p.rotary_sin == nullptr))
+    throw ArgError("If rotary cos is provided, rotary sin must also be provided");  // flash_api.cpp:1516
+  if (p.rotary_cos) {
+    if (!p.k_new)  // flash_api.cpp:1504
+      throw ArgError("If rotary cos/sin are provided, new key / value to be appended to KV cache must also be provided");
+    if (p.rotary_dim <= 0 || p.rotary_dim > p.head_dim) throw ArgError("rotary_dim must be <= headdim");
+    if (p.rotary_dim % 16 != 0)
+      throw ArgError("Only rotary dimensions divisible by 16 are currently supported");
+    if (p.seqlen_ro < p.seqlen_k) throw ArgError("cos/sin seqlen must be at least the seqlen of KV cache");
+    if ((reinterpret_cast<uintptr_t>(p.rotary_cos) | reinterpret_cast<uintptr_t>(p.rotary_sin)) & 15)
+      throw ArgError("[vattn] tensors must be 16-byte aligned");
+  }
   auto al = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
   if (!al(p.q) || !al(p.k_cache) || !al(p.v_cache) || !al(p.out) || (p.k_new && !al(p.k_new)) ||
       (p.v_new && !al(p.v_new)))
@@ -143,9 +159,11 @@ size_t workspace_for(const vattn_fwd_params_t& p, Path path) {
   }
 }
 
-void run_fwd(const vattn_fwd_params_t& p, cudaStream_t stream) {
-  validate(p);
-  if (p.batch == 0) return;
+void run_fwd(const vattn_fwd_params_t& p_in, cudaStream_t stream) {
+  validate(p_in);
+  if (p_in.batch == 0) return;
+  // rotary: q and k_new are rotated into the head of the workspace, everything below runs on those
+  const vattn_fwd_params_t p = p_in.rotary_cos ? launch_rope(p_in, stream) : p_in;
   const Path path = choose(p);
   // the tensor-core decode kernel appends a single new token itself; every other case uses the
   // separate append kernel
@@ -195,6 +213,10 @@ size_t vattn_fwd_kvcache_workspace(const vattn_fwd_params_t* p) {
   try {
     validate(*p);
     if (p->batch == 0) return 0;
+    if (p->rotary_cos) {
+      const vattn_fwd_params_t r = rope_rotated_view(*p, p->q, p->k_new);
+      return rope_workspace_bytes(*p) + workspace_for(r, choose(r));
+    }
     return workspace_for(*p, choose(*p));
   } catch (...) {
     translate_attn_exception();
@@ -271,6 +293,8 @@ int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* d
   try {
     if (prefill) validate(*prefill);
     if (decode) validate(*decode);
+    if ((prefill && prefill->rotary_cos) || (decode && decode->rotary_cos))
+      throw UnsupportedError("[vattn] the fused POD call takes no rotary arguments (fused_attn_interface.py:12-40)");
     if (pod_fused_path(prefill, decode)) {
       launch_pod_tc(*prefill, *decode, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
       return VATTN_OK;
