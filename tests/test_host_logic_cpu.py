@@ -244,3 +244,62 @@ def test_head_sharded_attention_allreduce_gloo_world2():
         assert p.exitcode == 0
     assert sorted(r for r, _ in res) == [0, 1]
     assert all(err < 1e-4 for _, err in res), res
+
+
+def test_block_space_manager_accounting_against_allocator():
+    """vattention_block_space_manager.py:9-98 mirror, fed from the allocator (mock driver): what the
+    scheduler admits never exceeds what step() can map."""
+    import torch
+    from vattention_b200 import _lib
+    from vattention_b200 import vattention as va
+    from vattention_b200.block_space_manager import vAttentionBlockSpaceManager
+
+    class Seq:
+        def __init__(self, i, n):
+            self.seq_id, self.n = i, n
+
+        def get_len(self):
+            return self.n
+
+    va._use_backend(_lib.BACKEND_HOST_MOCK)
+    try:
+        L, B, ctx = 2, 4, 32768
+        va.init_kvcache(L, 2, 64, B, ctx, 0, torch.float16, 2 << 20, False)
+        va.reserve_physical_pages(20 * (2 << 20))          # 20 pages = 5 blocks of 2L pages
+        tpp = va.get_config()["tokens_per_page"]
+        m = vAttentionBlockSpaceManager(tpp, 5, ctx, watermark=0.2)
+        assert m.watermark_blocks == 1
+        with pytest.raises(AttributeError):
+            m.can_append_slot()                              # free_blocks unset, as in the reference
+        assert m.refresh(va) == 5
+        a, b, c = Seq(0, 2 * tpp), Seq(1, tpp + 1), Seq(2, 1)
+        assert m.get_num_blocks(a) == 2 and m.get_num_blocks(b) == 2 and m.get_num_blocks(c) == 1
+        assert m.can_allocate(a)
+        m.allocate(a)
+        assert m.promised_blocks == 2 and m.is_allocated(a) and not m.is_allocated(b)
+        assert m.can_allocate(b)                             # 5 - 2 - 2 >= 1
+        m.allocate(b)
+        assert not m.can_allocate(c)                         # 5 - 4 - 1 < 1
+        assert m.can_append_slot()
+        # the allocator maps exactly what was promised
+        lens = [0] * B
+        for s in (a, b):
+            lens[va.alloc_new_batch_idx(s.n)] = s.n
+        va.step(lens, True)
+        assert m.refresh(va) == 1 and m.promised_blocks == 0
+        assert not m.can_append_slot() or m.free_blocks == 1
+        m.append_slot(a)                                     # 2*tpp -> 2*tpp+1 opens block 3
+        assert m.promised_blocks == 1 and not m.can_append_slot()
+        m.append_slot(b)                                     # tpp+1 -> tpp+2 stays inside block 2
+        assert m.promised_blocks == 1
+        m.free(a)
+        m.free(a)                                            # second free is a no-op
+        assert m.free_blocks == 3 and not m.is_allocated(a)
+        va.free_batch_idx(0)
+        assert m.refresh(va) == va.num_free_kvblocks() == 3  # deferred reclaim: a's pages count as free
+        assert m.get_block_table(b) is None and m.get_num_free_gpu_blocks(b) == 3
+        m.reset()
+        assert not m.is_allocated(b)
+    finally:
+        va.cleanup()
+        va._use_backend(_lib.BACKEND_CUDA)
