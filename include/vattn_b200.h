@@ -273,6 +273,23 @@ int vattn_fwd_kvcache_host_async(const vattn_fwd_params_t* p, void* stream);
 int vattn_allreduce_oneshot(const uint64_t* peer_partial_ptrs, const uint64_t* peer_flag_ptrs, void* out,
                             int64_t n_elems, int dtype, int rank, int world, uint32_t epoch, void* stream);
 
+/* The same collective fused with the GEMM that feeds it (the row-parallel o_proj,
+ * tensor_parallel/layers.py:432-461): out[tokens, hidden] = sum over ranks of
+ * x_r[tokens, k_local] . w_r[hidden, k_local]^T, ONE kernel per rank (csrc/oproj_allreduce.cu).
+ * x: this rank's attention output (row stride in elements), w: this rank's o_proj weight shard in
+ * nn.Linear layout [hidden, k_local] row-major.  peer_recv_ptrs[r] / peer_flag_ptrs[r]: rank r's
+ * receive area (vattn_oproj_allreduce_recv_bytes) and flag array (..._flag_bytes, zeroed once) in a
+ * symmetric allocation, as mapped in THIS process.  epoch_state: 4 zero-initialised uint32 in local
+ * device memory ([0] completed calls, [2] != 0 after a peer failed to arrive); the call sequence
+ * must be the same on every rank.  1..128 tokens, hidden % 128 == 0, k_local % 64 == 0;
+ * CUDA-graph capturable (no host-side epoch).                                                     */
+size_t vattn_oproj_allreduce_recv_bytes(int32_t max_tokens, int32_t hidden, int32_t world);
+size_t vattn_oproj_allreduce_flag_bytes(int32_t hidden);
+int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, void* out, int32_t tokens,
+                          int32_t hidden, int32_t k_local, int32_t dtype, int32_t max_tokens,
+                          const uint64_t* peer_recv_ptrs, const uint64_t* peer_flag_ptrs,
+                          uint32_t* epoch_state, int32_t rank, int32_t world, void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's
  * `gpu_launches` counts from here) */
 uint64_t vattn_launch_count(void);

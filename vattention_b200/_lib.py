@@ -122,6 +122,11 @@ _SIGS = {
     "vattn_fwd_kvcache_host_async": (C.c_int, [_P(FwdParams), C.c_void_p]),
     "vattn_allreduce_oneshot": (C.c_int, [_P(C.c_uint64), _P(C.c_uint64), C.c_void_p, C.c_int64, C.c_int,
                                           C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
+    "vattn_oproj_allreduce_recv_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "vattn_oproj_allreduce_flag_bytes": (C.c_size_t, [C.c_int32]),
+    "vattn_oproj_allreduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, _P(C.c_uint64), _P(C.c_uint64),
+                                        C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "vattn_launch_count": (C.c_uint64, []),
     "vattn_kernel_timing": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_uint64)]),
     "vattn_selftest_umma": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p]),

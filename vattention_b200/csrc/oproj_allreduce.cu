@@ -1,0 +1,314 @@
+// Row-parallel o_proj GEMM fused with its all-reduce over NVLink peer memory.
+//
+// Reference: the step right after attention under tensor parallelism is
+//     partial = attn_out[tokens, Hq/tp * D] @ W_o_shard^T ;  all_reduce(partial)
+// (sarathi/model_executor/parallel_utils/tensor_parallel/layers.py:432-461 -> mappings.py:16-26:
+// a cuBLAS GEMM, then NCCL).  Here it is ONE kernel per rank:
+//
+//   * CTA t owns hidden columns [128 t, 128 t + 128).  tcgen05: the weight rows are the MMA's M
+//     axis (W_o_shard is [hidden, K] K-major, exactly nn.Linear's layout), the tokens its N axis
+//     (<= 128, zero-filled to a multiple of 16 by TMA), the accumulator D^T[128 x tokens] lives in
+//     TMEM.  One TMA warp streams [128 x 64] weight atoms + the [tokens x 64] activation atom
+//     through a 4-stage ring, one thread issues the MMAs.
+//   * epilogue (4 warps = 128 TMEM lanes): accumulator -> bf16 -> shared memory (transposed back
+//     to [token][hidden]) -> 16-byte stores of the tile into EVERY rank's receive slot
+//     recv[parity][my_rank] over NVLink -> system fence -> per-tile flag on every rank;
+//   * the same CTA then waits for the `world` flags of ITS tile, sums the `world` slots (local
+//     memory, fixed rank order so every rank gets bit-identical sums) and writes out[tokens, hidden].
+//   The tiles are independent, so the exchange of tile t overlaps the weight streaming of the
+//   other tiles; no separate collective launch, no partial round trip through HBM.
+//
+// Epochs live in device memory (epoch_state[0] = last completed call) so the launch is CUDA-graph
+// capturable; the receive slots and flags are double buffered on epoch parity.  Reuse is safe: a
+// rank writes parity e & 1 again in call e + 2, after its own call e + 1 finished, in which it
+// saw every peer's flag e + 1, which a peer only publishes after ITS call e (the last reader of
+// that parity) completed -- launches on one stream run in order.
+// Roofline: HBM (weights 2 K hidden bytes read once per rank; decode tokens <= 128 => ~1 FLOP/B
+// per token row); the exchange moves (world - 1) * tokens * hidden * 2 bytes per rank over NVLink.
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "attn_common.cuh"
+#include "capi_common.h"
+#include "sm100_ptx.cuh"
+#include "tma_desc.h"
+
+namespace vattn {
+
+namespace {
+using namespace ptx;
+
+constexpr int kMaxWorld = 8;
+constexpr int kTileH = 128;     // hidden columns per CTA (MMA M)
+constexpr int kKStep = 64;      // K elements per ring stage (one 128-byte swizzle atom)
+constexpr int kStages = 4;
+constexpr int kMaxTokens = 128;
+constexpr int kThreads = 192;   // warps 0-3 epilogue, 4 TMA, 5 MMA
+constexpr uint32_t kSpinLimit = 1u << 22;
+
+struct OprojParams {
+  char* recv[kMaxWorld];       // rank r's receive area: [2][world][max_tokens][hidden]
+  uint32_t* flags[kMaxWorld];  // rank r's flags: [2][n_tiles][kMaxWorld]
+  char* out;                   // [tokens, hidden]
+  uint32_t* epoch_state;       // [0] last completed epoch, [1] CTAs done, [2] error (spin limit hit)
+  int tokens, tokens_pad, hidden, k_steps, max_tokens, rank, world;
+};
+
+struct __align__(1024) OprojSmem {
+  uint8_t w[kStages][kTileH * 128];      // [128 rows x 128 B] SW128 atoms
+  uint8_t x[kStages][kMaxTokens * 128];  // [tokens_pad rows x 128 B]
+  uint8_t tile[kMaxTokens * kTileH * 2]; // epilogue staging [token][hidden] 16-bit
+  uint64_t full[kStages], empty[kStages], acc_full;
+  uint32_t tmem_base, epoch;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_sys_128(const void* p) {  // written by a peer GPU: not through L1
+  uint4 r;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_sys_128(void* p, const uint4& v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap x_map,
+                       const OprojParams p) {
+  extern __shared__ uint8_t raw[];
+  OprojSmem& sm = *reinterpret_cast<OprojSmem*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const uint32_t tmem_cols = p.tokens_pad <= 32 ? 32 : p.tokens_pad <= 64 ? 64 : 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    mbar_init(&sm.acc_full, 1);
+    fence_mbar_init();
+    sm.epoch = *reinterpret_cast<volatile uint32_t*>(p.epoch_state) + 1;
+  }
+  if (warp == 5) {
+    tmem_alloc(&sm.tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == 4 && lane == 0) {
+    prefetch_tensormap(&w_map);
+    prefetch_tensormap(&x_map);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t epoch = sm.epoch;
+  const int parity = epoch & 1;
+
+  if (warp == 4) {
+    // ---- TMA producer
+    if (lane == 0) {
+      const uint32_t bytes = kTileH * 128 + p.tokens_pad * 128;
+      for (int k = 0; k < p.k_steps; k++) {
+        const int s = k % kStages;
+        if (k >= kStages) mbar_wait(&sm.empty[s], ((k / kStages) - 1) & 1);
+        mbar_expect_tx(&sm.full[s], bytes);
+        tma_load_2d(sm.w[s], &w_map, &sm.full[s], k * kKStep, tile * kTileH);
+        tma_load_2d(sm.x[s], &x_map, &sm.full[s], k * kKStep, 0);
+      }
+    }
+  } else if (warp == 5) {
+    // ---- MMA issuer: D^T[128 hidden x tokens_pad] += W[128 x 64] . X[tokens_pad x 64]^T
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(std::is_same<T, __half>::value ? kFmtF16 : kFmtBF16, kTileH,
+                                        (uint32_t)p.tokens_pad, 0, 0);
+      for (int k = 0; k < p.k_steps; k++) {
+        const int s = k % kStages;
+        mbar_wait(&sm.full[s], (k / kStages) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sm.w[s]), b0 = smem_u32(sm.x[s]);
+#pragma unroll
+        for (int j = 0; j < kKStep / 16; j++)
+          umma_ss(tmem, make_smem_desc(a0 + j * 32, 16, 1024, kLayoutSw128),
+                  make_smem_desc(b0 + j * 32, 16, 1024, kLayoutSw128), idesc, (k | j) != 0);
+        umma_commit(&sm.empty[s]);
+      }
+      umma_commit(&sm.acc_full);
+    }
+  } else {
+    // ---- epilogue warps 0-3: TMEM lane = hidden column of the tile
+    const int t = threadIdx.x;  // 0..127
+    mbar_wait(&sm.acc_full, 0);
+    tc_fence_after();
+    T* stage = reinterpret_cast<T*>(sm.tile);
+    for (int c0 = 0; c0 < p.tokens_pad; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_x16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; j++)
+        if (c0 + j < p.tokens) stage[(c0 + j) * kTileH + t] = Elem<T>::from_f(__uint_as_float(r[j]));
+    }
+    tc_fence_before();
+    named_bar_sync(1, 128);
+    // push the tile into every rank's slot [parity][my rank]
+    const int n_vec = p.tokens * (kTileH * 2 / 16);  // 16 vectors per token row of the tile
+    const size_t slot = (size_t)p.max_tokens * p.hidden * 2;
+    const size_t my_slot = ((size_t)parity * p.world + p.rank) * slot;
+    for (int v = t; v < n_vec; v += 128) {
+      const int tok = v >> 4, seg = v & 15;
+      const uint4 val = *reinterpret_cast<const uint4*>(sm.tile + (size_t)tok * (kTileH * 2) + seg * 16);
+      const size_t off = my_slot + ((size_t)tok * p.hidden + (size_t)tile * kTileH) * 2 + seg * 16;
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; r++)
+        if (r < p.world) st_sys_128(p.recv[r] + off, val);
+    }
+    __threadfence_system();
+    named_bar_sync(1, 128);
+    const size_t flag_row = ((size_t)parity * gridDim.x + tile) * kMaxWorld;
+    if (t < p.world) {
+      st_release_sys_u32(p.flags[t] + flag_row + p.rank, epoch);
+      const uint32_t* mine = p.flags[p.rank] + flag_row + t;
+      uint32_t spins = 0;
+      while ((int32_t)(ld_acquire_sys_u32(mine) - epoch) < 0) {
+        if (++spins > kSpinLimit) {  // a peer never arrived: fail visibly instead of hanging the GPU
+          p.epoch_state[2] = 1;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    named_bar_sync(1, 128);
+    // reduce the `world` slots of this tile, rank order, fp32
+    const char* base = p.recv[p.rank] + (size_t)parity * p.world * slot;
+    for (int v = t; v < n_vec; v += 128) {
+      const int tok = v >> 4, seg = v & 15;
+      const size_t off = ((size_t)tok * p.hidden + (size_t)tile * kTileH) * 2 + seg * 16;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; r++) {
+        if (r >= p.world) break;
+        const uint4 u = ld_sys_128(base + (size_t)r * slot + off);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float2 f = Elem<T>::to_f2(w[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+      uint4 o;
+      o.x = Elem<T>::from_f2(acc[0], acc[1]);
+      o.y = Elem<T>::from_f2(acc[2], acc[3]);
+      o.z = Elem<T>::from_f2(acc[4], acc[5]);
+      o.w = Elem<T>::from_f2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(p.out + off) = o;
+    }
+  }
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, tmem_cols);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t done = atomicAdd(p.epoch_state + 1, 1u);
+    if (done == gridDim.x - 1) {  // last CTA of this call: publish the epoch for the next launch
+      p.epoch_state[1] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(p.epoch_state) = epoch;
+    }
+  }
+}
+
+}  // namespace
+
+}  // namespace vattn
+
+using namespace vattn;
+
+extern "C" {
+
+size_t vattn_oproj_allreduce_recv_bytes(int32_t max_tokens, int32_t hidden, int32_t world) {
+  return (size_t)2 * world * max_tokens * hidden * 2;
+}
+size_t vattn_oproj_allreduce_flag_bytes(int32_t hidden) {
+  return (size_t)2 * (hidden / kTileH) * kMaxWorld * sizeof(uint32_t);
+}
+
+int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, void* out, int32_t tokens,
+                          int32_t hidden, int32_t k_local, int32_t dtype, int32_t max_tokens,
+                          const uint64_t* peer_recv_ptrs, const uint64_t* peer_flag_ptrs,
+                          uint32_t* epoch_state, int32_t rank, int32_t world, void* stream) {
+  try {
+    if (!x || !w || !out || !peer_recv_ptrs || !peer_flag_ptrs || !epoch_state)
+      throw ArgError("[vattn] oproj_allreduce: null pointer");
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+      throw ArgError("[vattn] oproj_allreduce: world must be 1..8 and rank inside it");
+    if (dtype != VATTN_DTYPE_F16 && dtype != VATTN_DTYPE_BF16)
+      throw ArgError("[vattn] oproj_allreduce: fp16/bf16 only");
+    if (tokens <= 0 || tokens > kMaxTokens || tokens > max_tokens)
+      throw UnsupportedError("[vattn] oproj_allreduce: 1..128 tokens per call (decode batches); larger "
+                             "batches use the GEMM + all-reduce pair");
+    if (hidden % kTileH != 0 || hidden / kTileH > 148 || k_local % kKStep != 0 || k_local <= 0)
+      throw UnsupportedError("[vattn] oproj_allreduce: hidden must be a multiple of 128 (<= 18944) and "
+                             "the local K a multiple of 64");
+    if (x_row_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
+        (reinterpret_cast<uintptr_t>(out) & 15))
+      throw ArgError("[vattn] oproj_allreduce: tensors must be 16-byte aligned");
+    OprojParams p;
+    for (int r = 0; r < kMaxWorld; r++) {
+      p.recv[r] = r < world ? reinterpret_cast<char*>(peer_recv_ptrs[r]) : nullptr;
+      p.flags[r] = r < world ? reinterpret_cast<uint32_t*>(peer_flag_ptrs[r]) : nullptr;
+    }
+    p.out = static_cast<char*>(out);
+    p.epoch_state = epoch_state;
+    p.tokens = tokens;
+    p.tokens_pad = (tokens + 15) / 16 * 16;
+    p.hidden = hidden;
+    p.k_steps = k_local / kKStep;
+    p.max_tokens = max_tokens;
+    p.rank = rank, p.world = world;
+    const CUtensorMap w_map = make_kmajor_map(w, hidden, k_local, (int64_t)k_local * 2, kTileH);
+    const CUtensorMap x_map = make_kmajor_map(x, tokens, k_local, x_row_stride * 2, p.tokens_pad);
+    const size_t smem = sizeof(OprojSmem) + 1024;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == VATTN_DTYPE_BF16) {
+      VATTN_CUDA(cudaFuncSetAttribute(oproj_allreduce_kernel<__nv_bfloat16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      oproj_allreduce_kernel<__nv_bfloat16><<<hidden / kTileH, kThreads, smem, s>>>(w_map, x_map, p);
+    } else {
+      VATTN_CUDA(cudaFuncSetAttribute(oproj_allreduce_kernel<__half>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      oproj_allreduce_kernel<__half><<<hidden / kTileH, kThreads, smem, s>>>(w_map, x_map, p);
+    }
+    count_launch();
+    VATTN_CUDA(cudaGetLastError());
+    return VATTN_OK;
+  } catch (const ArgError& e) {
+    g_last_error = e.what();
+    return VATTN_ERR_INVALID;
+  } catch (const UnsupportedError& e) {
+    g_last_error = e.what();
+    return VATTN_ERR_UNSUPPORTED;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return VATTN_ERR_DRIVER;
+  }
+}
+
+}  // extern "C"

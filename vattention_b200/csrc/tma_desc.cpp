@@ -39,6 +39,21 @@ CUtensorMap make_headdim128_map(const void* base, int64_t seq_extent, int64_t he
   return m;
 }
 
+CUtensorMap make_kmajor_map(const void* base, int64_t rows, int64_t cols, int64_t row_stride_bytes, int box_rows) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_stride_bytes)};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("[vattn] cuTensorMapEncodeTiled (2-D) failed (" + std::to_string((int)r) +
+                             "): base/strides must be 16-byte aligned");
+  return m;
+}
+
 int safe_tail_rows(int64_t pitch) {
   if (pitch <= 0) return 0;
   if (16384 % pitch == 0) return 128;

@@ -17,6 +17,10 @@ CUtensorMap make_headdim128_map(const void* base, int64_t seq_extent, int64_t he
                                 int64_t row_stride_bytes, int64_t head_stride_bytes,
                                 int64_t batch_stride_bytes, int box_rows, int box_atoms = 2);
 
+// 2-D map over a [rows, cols] 16-bit K-major operand (GEMM A or B): one box of (64 cols, box_rows)
+// lands as a [box_rows x 128 B] SWIZZLE_128B atom column; rows past `rows` are zero-filled.
+CUtensorMap make_kmajor_map(const void* base, int64_t rows, int64_t cols, int64_t row_stride_bytes, int box_rows);
+
 // rows per TMA box that can never reach past a request's mapped prefix: 128 when the row pitch
 // divides 16 KB (tokens_per_page is a multiple of 128), otherwise the largest power of two <= 128
 // dividing tokens_per_page = 2 MiB / pitch (megacache views).  0 = layout not usable with TMA.

@@ -160,3 +160,88 @@ class HeadShardedAttentionPeer(HeadShardedAttention):
         tokens = flat.shape[0]
         torch.matmul(flat, self.w_o, out=self.ar.partial_buffer(tokens))
         return self.ar.reduce(tokens)
+
+
+class FusedOProjAllReduce:
+    """o_proj GEMM and its all-reduce as ONE kernel per rank (csrc/oproj_allreduce.cu): tcgen05 GEMM
+    with the weight rows on the MMA M axis, each finished [tokens x 128] tile pushed straight into
+    every rank's receive slot over NVLink, flagged, and summed by the CTA that owns the tile.
+
+    `w_shard` is this rank's slice in nn.Linear layout [hidden, k_local] (RowParallelLinear.weight,
+    tensor_parallel/layers.py:432-447).  With `local_only=True` (or no process group) the symmetric
+    allocation is a plain local tensor and world = 1: the GEMM path alone, used by single-GPU tests.
+    Decode batches only (<= 128 tokens per call); the call is CUDA-graph capturable.
+    """
+
+    MAX_TOKENS = 128
+
+    def __init__(self, w_shard: torch.Tensor, max_tokens: int, group: Optional[dist.ProcessGroup] = None,
+                 local_only: bool = False):
+        import ctypes as C
+
+        from . import _lib
+        self._C, self._lib = C, _lib
+        if w_shard.dim() != 2 or not w_shard.is_contiguous():
+            raise ValueError("w_shard must be a contiguous [hidden, k_local] tensor")
+        if max_tokens > self.MAX_TOKENS:
+            raise ValueError("FusedOProjAllReduce handles at most 128 tokens per call")
+        self.w = w_shard
+        self.hidden, self.k_local = w_shard.shape
+        self.max_tokens, self.dtype, self.device = max_tokens, w_shard.dtype, w_shard.device
+        self._dt = {torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}[self.dtype]
+        lib = _lib.lib
+        if local_only or not dist.is_initialized():
+            self.rank, self.world, self.group = 0, 1, None
+        else:
+            self.group = group or dist.group.WORLD
+            self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.recv_bytes = (lib.vattn_oproj_allreduce_recv_bytes(max_tokens, self.hidden, self.world) + 255) // 256 * 256
+        self.flag_bytes = lib.vattn_oproj_allreduce_flag_bytes(self.hidden)
+        total = self.recv_bytes + self.flag_bytes
+        if self.world == 1:
+            self.buf = torch.zeros(total, dtype=torch.uint8, device=self.device)
+            bases = [self.buf.data_ptr()]
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buf = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+            self.buf.zero_()
+            torch.cuda.synchronize(self.device)
+            self.handle = symm_mem.rendezvous(self.buf, self.group.group_name)
+            dist.barrier(self.group)      # every rank's flags are zero before anyone publishes
+            bases = [int(p) for p in self.handle.buffer_ptrs]
+        self._recv = (C.c_uint64 * self.world)(*bases)
+        self._flags = (C.c_uint64 * self.world)(*[b + self.recv_bytes for b in bases])
+        self.epoch_state = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self.out = torch.empty(max_tokens, self.hidden, dtype=self.dtype, device=self.device)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """x [tokens, k_local] (row stride free) -> all-reduced [tokens, hidden] (a view of an
+        internal buffer, valid until the next call)."""
+        tokens = x.shape[0]
+        if x.dim() != 2 or x.shape[1] != self.k_local or x.stride(1) != 1 or x.dtype != self.dtype:
+            raise ValueError("x must be [tokens, k_local] with unit inner stride and the weight's dtype")
+        out = self.out[:tokens]
+        C = self._C
+        self._lib.check(self._lib.lib.vattn_oproj_allreduce(
+            x.data_ptr(), x.stride(0), self.w.data_ptr(), out.data_ptr(), tokens, self.hidden, self.k_local,
+            self._dt, self.max_tokens, self._recv, self._flags, self.epoch_state.data_ptr(), self.rank,
+            self.world, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
+
+    def failed(self) -> bool:
+        """True after a call gave up waiting for a peer (device-side spin limit); synchronises."""
+        return bool(self.epoch_state[2].item())
+
+
+class HeadShardedAttentionFused(HeadShardedAttention):
+    """HeadShardedAttention whose o_proj + all-reduce is the fused kernel."""
+
+    def __init__(self, shard: HeadShard, w_o_shard: torch.Tensor, attn_fn, max_tokens: int,
+                 group: Optional[dist.ProcessGroup] = None):
+        super().__init__(shard, w_o_shard, attn_fn, group)
+        # HeadShard.shard_o_proj hands out [k_local, hidden]; the kernel streams nn.Linear's [hidden, k_local]
+        self.op = FusedOProjAllReduce(w_o_shard.t().contiguous(), max_tokens, group)
+
+    def forward(self, q_shard: torch.Tensor, *attn_args, **attn_kwargs) -> torch.Tensor:
+        out = self.attn_fn(q_shard, *attn_args, **attn_kwargs)
+        return self.op(out.reshape(out.shape[0] * out.shape[1], -1))
