@@ -128,12 +128,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from vattention_b200 import attention as att
     from vattention_b200 import vattention as va
-    from vattention_b200.tp import HeadShard, HeadShardedAttention, HeadShardedAttentionPeer
+    from vattention_b200.tp import (HeadShard, HeadShardedAttention, HeadShardedAttentionFused,
+                                    HeadShardedAttentionPeer)
 
     shard = HeadShard(rank, world, HQ, HKV, D)
     hq, hkv = shard.heads_per_rank, shard.kv_heads_per_rank
     K, W = args.steps, args.warmup
-    total_steps = W + K + (W + K if not args.no_e2e else 0) + 2
+    total_steps = W + K + (W + K if not args.no_e2e else 0) + 2 + (K + 2 if world > 1 else 0)
     start_len = CTX - total_steps - 1           # every sequence ends the run at <= CTX tokens
     assert start_len > 0
     torch.zeros(1, device=dev)                  # context for the allocator (cudaInternal.h:19-25)
@@ -162,7 +163,9 @@ def run_ours(args):
     tp_attn = None
     if world > 1:
         # the o_proj all-reduce: our one-shot kernel over NVLink peer memory (default) or NCCL
-        if args.tp_collective == "peer":
+        if args.tp_collective == "fused":
+            tp_attn = HeadShardedAttentionFused(shard, w_o, att.flash_attn_with_kvcache, max_tokens=BATCH)
+        elif args.tp_collective == "peer":
             tp_attn = HeadShardedAttentionPeer(shard, w_o, att.flash_attn_with_kvcache, max_tokens=BATCH)
         else:
             tp_attn = HeadShardedAttention(shard, w_o, att.flash_attn_with_kvcache)
@@ -193,10 +196,49 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # N > 1: the per-rank kernels are 8x shorter, so the 32 layer-calls of a decode iteration are
+    # launch-bound from Python; capture them once in a CUDA graph (lengths live in a device tensor the
+    # graph increments, K/V views span the whole virtual tensor so shapes do not change per step)
+    use_graph = world > 1 and args.tp_graph and args.tp_collective in ("fused", "nccl")
+    eager_step = one_step
+    graph_launches = 0
+    if use_graph:
+        cs = torch.full((BATCH,), seq_lens[0], dtype=torch.int32, device=dev)
+
+        def layers_body():
+            for layer in range(LAYERS):
+                out = tp_attn.forward(q[layer], k_layers[layer % n_res], v_layers[layer % n_res], kn[layer],
+                                      vn[layer], cache_seqlens=cs, cache_batch_idx=batch_idx,
+                                      softmax_scale=scale, causal=True)
+            sink.add_(out.flatten()[0].float())
+            cs.add_(1)
+
+        seq_lens = [n + 1 for n in seq_lens]       # one eager iteration (loads modules, sizes workspaces)
+        va.step_async(seq_lens)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            layers_body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        barrier()
+        graph = torch.cuda.CUDAGraph()
+        n0 = att.launch_count()
+        with torch.cuda.graph(graph):
+            layers_body()
+        graph_launches = att.launch_count() - n0
+        barrier()
+
+        def one_step(lens_now):                    # noqa: F811 -- the graph-replay flavour of one_step
+            new_lens = [n + 1 for n in lens_now]
+            va.step_async(new_lens)
+            graph.replay()
+            return new_lens
+
     for _ in range(W):
         seq_lens = one_step(seq_lens)
     barrier()
-    att.kernel_timing(1)
+    if not use_graph:
+        att.kernel_timing(1)
     launches0 = att.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -208,9 +250,19 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
+    launches = att.launch_count() - launches0 + graph_launches * K
+    if use_graph:
+        # events cannot be read back from inside a graph: the per-launch kernel time for the roofline
+        # comes from K eager iterations of the same step right after the timed region
+        cs_lens = seq_lens
+        att.kernel_timing(1)
+        for _ in range(K):
+            cs_lens = eager_step(cs_lens)
+        barrier()
+        seq_lens = cs_lens
+        cs.fill_(seq_lens[0])
     kern_ms, kern_n = att.kernel_timing(2)
     att.kernel_timing(0)
-    launches = att.launch_count() - launches0
     alloc_stats = va.get_step_stats()
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -292,6 +344,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(sample_seqs=args.cpu_sample_seqs, budget_s=args.cpu_budget_s)
 
+    if world > 1 and args.tp_collective == "fused" and tp_attn.op.failed():
+        raise RuntimeError("fused o_proj + all-reduce: a peer did not arrive (device-side spin limit)")
     va.cleanup()
     if rank == 0:
         line = {
@@ -303,9 +357,13 @@ def run_ours(args):
             "config": {"workload": "decode32k", "shapes": f"B{BATCH} Hq{HQ} Hkv{HKV} D{D} L{LAYERS} ctx{CTX}",
                        "backend": "fa_vattn_2mb (vAttention virtual tensors, 2 MiB pages, step_async)",
                        "resident_layers": n_res, "parallelism": f"tp{world}" if world > 1 else "single",
-                       "collective": (f"o_proj all-reduce [64,{HIDDEN}] bf16 per layer-call: " + (
-                           "one-shot kernel over NVLink peer memory (csrc/tp_allreduce.cu)"
-                           if args.tp_collective == "peer" else "NCCL")) if world > 1 else None,
+                       "collective": (f"o_proj + all-reduce [64,{HIDDEN}] bf16 per layer-call: " + {
+                           "fused": "ONE kernel: tcgen05 GEMM, tiles pushed over NVLink peer memory and "
+                                    "reduced in place (csrc/oproj_allreduce.cu)",
+                           "peer": "cuBLAS GEMM + one-shot all-reduce kernel over NVLink peer memory "
+                                   "(csrc/tp_allreduce.cu)",
+                           "nccl": "cuBLAS GEMM + NCCL all-reduce"}[args.tp_collective]) if world > 1 else None,
+                       "cuda_graph": bool(use_graph),
                        "l2": "each layer-call streams 8.6 GB of K/V (>> 126 MB L2); no flush needed",
                        "ms_per_layer_call": round(ms / K / LAYERS, 4)},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
@@ -445,7 +503,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "fa_vattn"])
     ap.add_argument("--resident-layers", type=int, default=4)
-    ap.add_argument("--tp-collective", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--tp-collective", default="peer", choices=["fused", "peer", "nccl"])
+    ap.add_argument("--no-tp-graph", dest="tp_graph", action="store_false",
+                    help="N > 1: launch the 32 layer-calls eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=2)

@@ -45,7 +45,7 @@ constexpr int kKStep = 64;      // K elements per ring stage (one 128-byte swizz
 constexpr int kStages = 4;
 constexpr int kMaxTokens = 128;
 constexpr int kThreads = 192;   // warps 0-3 epilogue, 4 TMA, 5 MMA
-constexpr uint32_t kSpinLimit = 1u << 22;
+constexpr uint32_t kSpinLimit = 1u << 24;  // ~20 s of polling before giving up on a peer
 
 struct OprojParams {
   char* recv[kMaxWorld];       // rank r's receive area: [2][world][max_tokens][hidden]
