@@ -281,7 +281,7 @@ int vattn_allreduce_oneshot(const uint64_t* peer_partial_ptrs, const uint64_t* p
  * receive area (vattn_oproj_allreduce_recv_bytes) and flag array (..._flag_bytes, zeroed once) in a
  * symmetric allocation, as mapped in THIS process.  epoch_state: 4 zero-initialised uint32 in local
  * device memory ([0] completed calls, [2] != 0 after a peer failed to arrive); the call sequence
- * must be the same on every rank.  1..128 tokens, hidden % 128 == 0, k_local % 64 == 0;
+ * must be the same on every rank.  1..128 tokens, hidden % 32 == 0, k_local % 64 == 0;
  * CUDA-graph capturable (no host-side epoch).                                                     */
 size_t vattn_oproj_allreduce_recv_bytes(int32_t max_tokens, int32_t hidden, int32_t world);
 size_t vattn_oproj_allreduce_flag_bytes(int32_t hidden);

@@ -321,9 +321,12 @@ def test_against_flash_attn_library_if_present():
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_pod_fused_many_items_matches_oracle(dtype):
-    """Enough prefill row blocks and decode chunks that every persistent CTA of the fused kernel
-    runs several work items of both kinds (barrier re-initialisation, TMEM reuse, ticket order)."""
+@pytest.mark.parametrize("fused_params", [15, 9])
+def test_pod_fused_many_items_matches_oracle(dtype, fused_params):
+    """fused_params 9 (an explicit configuration) = the persistent fused kernel: enough prefill row
+    blocks and decode chunks that every CTA runs several work items of both kinds (barrier
+    re-initialisation, TMEM reuse, ticket order).  15 (auto) = the two specialised kernels
+    co-scheduled on two streams with a fork/join inside the call."""
     g = torch.Generator().manual_seed(77)
     Hq, Hkv, D = 8, 2, 128
     Bp, Sq, Sk = 2, 700, 1500
@@ -347,7 +350,8 @@ def test_pod_fused_many_items_matches_oracle(dtype):
     for _ in range(2):  # second call re-uses the zeroed ticket counter slot in the workspace
         out_p, out_d = att.true_fused_attn_with_kvcache(
             d(q_p), d(kc_p), d(vc_p), d(q_d), kd, vd, d(kn), d(vn), causal=True,
-            cache_seqlens_p=d(lens_p), cache_seqlens_d=d(lens_d), cache_batch_idx=d(idx), fused_params=15)
+            cache_seqlens_p=d(lens_p), cache_seqlens_d=d(lens_d), cache_batch_idx=d(idx),
+            fused_params=fused_params)
         torch.cuda.synchronize()
         close(out_p, want_p, dtype)
         close(out_d, want_d, dtype)

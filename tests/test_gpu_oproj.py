@@ -27,7 +27,7 @@ def check(got, want, dtype):
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("tokens,hidden,k", [(64, 4096, 512), (1, 4096, 2048), (50, 1024, 128), (128, 4096, 4096),
-                                             (17, 256, 64), (96, 8192, 1024)])
+                                             (17, 256, 64), (96, 8192, 1024), (64, 11008, 256), (8, 160, 64)])
 def test_gemm_matches_fp32_reference(dtype, tokens, hidden, k):
     g = torch.Generator(device=DEV).manual_seed(tokens * 7 + k)
     w = (torch.randn(hidden, k, device=DEV, generator=g) * 0.05).to(dtype)
@@ -83,6 +83,6 @@ def test_argument_rules():
         op(torch.zeros(4, 256, device=DEV, dtype=torch.bfloat16))
     with pytest.raises(ValueError):
         FusedOProjAllReduce(w, 256, local_only=True)
-    with pytest.raises(RuntimeError, match="multiple of 128"):
+    with pytest.raises(RuntimeError, match="multiple of 32"):
         FusedOProjAllReduce(torch.zeros(200, 512, device=DEV, dtype=torch.bfloat16), 64, local_only=True)(
             torch.zeros(4, 512, device=DEV, dtype=torch.bfloat16))

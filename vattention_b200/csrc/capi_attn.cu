@@ -10,6 +10,7 @@
 // keys on the MMA M axis so a 32 KB K tile costs 64 tensor cycles.
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "attn_common.cuh"
@@ -274,45 +275,105 @@ size_t vattn_pod_workspace(const vattn_fwd_params_t* prefill, const vattn_fwd_pa
   try {
     if (prefill) validate(*prefill);
     if (decode) validate(*decode);
-    if (pod_fused_path(prefill, decode)) return pod_tc_workspace(*prefill, *decode);
   } catch (...) {
     translate_attn_exception();
     return 0;
   }
+  // enough for every strategy of vattn_pod_fwd: the persistent kernel or the two separate calls
   size_t a = prefill ? vattn_fwd_kvcache_workspace(prefill) : 0;
   size_t b = decode ? vattn_fwd_kvcache_workspace(decode) : 0;
   a = (a + 255) / 256 * 256;
-  return a + b;
+  size_t fused = 0;
+  try {
+    if (pod_fused_path(prefill, decode)) fused = pod_tc_workspace(*prefill, *decode);
+  } catch (...) {
+    translate_attn_exception();
+  }
+  return a + b > fused ? a + b : fused;
 }
+
+namespace {
+// side stream + fork/join events per caller stream for the co-scheduled POD strategy
+struct PodSide {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+PodSide& pod_side_for(cudaStream_t main) {
+  static std::mutex mu;
+  static std::unordered_map<cudaStream_t, PodSide> sides;
+  std::lock_guard<std::mutex> g(mu);
+  PodSide& s = sides[main];
+  if (!s.side) {
+    VATTN_CUDA(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+    VATTN_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    VATTN_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  return s;
+}
+enum class PodStrategy { Streams, Kernel, Serial };
+PodStrategy pod_strategy(int32_t fused_params) {
+  // the reference: 15 = "pick the most suitable" (fused_api.cpp:24-53), anything else names one
+  // tile configuration of its fused kernel.  Here: 15 -> the fastest measured arrangement, which is
+  // the two specialised kernels co-scheduled on two streams (SM-level overlap by the block
+  // scheduler; bench_extra.py pod: 1.13x over serial on a balanced hybrid batch where the
+  // persistent single kernel is 0.89x); an explicit configuration -> the persistent fused kernel.
+  // VATTN_POD_STRATEGY=streams|kernel|serial overrides.
+  if (const char* e = std::getenv("VATTN_POD_STRATEGY")) {
+    const std::string v(e);
+    if (v == "kernel") return PodStrategy::Kernel;
+    if (v == "serial") return PodStrategy::Serial;
+    if (v == "streams") return PodStrategy::Streams;
+  }
+  return fused_params == 15 ? PodStrategy::Streams : PodStrategy::Kernel;
+}
+}  // namespace
 
 int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode,
                   int32_t fused_params, void* workspace, size_t workspace_bytes, void* stream) {
-  // fused_params selects tile shapes / the HFuse baseline in the reference (fused_api.cpp:24-53);
-  // there is one schedule here, the value is accepted for signature compatibility
-  (void)fused_params;
   try {
     if (prefill) validate(*prefill);
     if (decode) validate(*decode);
     if ((prefill && prefill->rotary_cos) || (decode && decode->rotary_cos))
       throw UnsupportedError("[vattn] the fused POD call takes no rotary arguments (fused_attn_interface.py:12-40)");
-    if (pod_fused_path(prefill, decode)) {
-      launch_pod_tc(*prefill, *decode, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    cudaStream_t main = static_cast<cudaStream_t>(stream);
+    const PodStrategy strat = pod_strategy(fused_params);
+    if (strat == PodStrategy::Kernel && pod_fused_path(prefill, decode)) {
+      launch_pod_tc(*prefill, *decode, workspace, workspace_bytes, main);
       return VATTN_OK;
     }
-    // one side missing, or a shape the tensor-core path does not take: the two calls back to back
+    // the two specialised kernels: co-scheduled on two streams, or back to back (one side missing,
+    // serial requested)
     size_t a = prefill ? vattn_fwd_kvcache_workspace(prefill) : 0;
     a = (a + 255) / 256 * 256;
-    if (prefill) {
-      vattn_fwd_params_t p = *prefill;
-      p.workspace = workspace;
-      p.workspace_bytes = a;
-      run_fwd(p, static_cast<cudaStream_t>(stream));
-    }
+    const bool both = prefill && decode && prefill->batch > 0 && decode->batch > 0;
+    const bool fork = both && strat != PodStrategy::Serial;
+    PodSide* side = fork ? &pod_side_for(main) : nullptr;
     if (decode) {
       vattn_fwd_params_t d = *decode;
       d.workspace = workspace ? static_cast<char*>(workspace) + a : nullptr;
       d.workspace_bytes = workspace_bytes > a ? workspace_bytes - a : 0;
-      run_fwd(d, static_cast<cudaStream_t>(stream));
+      if (fork) {
+        VATTN_CUDA(cudaEventRecord(side->fork, main));
+        VATTN_CUDA(cudaStreamWaitEvent(side->side, side->fork, 0));
+        run_fwd(d, side->side);
+        VATTN_CUDA(cudaEventRecord(side->join, side->side));
+      } else if (!prefill) {
+        run_fwd(d, main);
+      }
+    }
+    if (prefill) {
+      vattn_fwd_params_t p = *prefill;
+      p.workspace = workspace;
+      p.workspace_bytes = a;
+      run_fwd(p, main);
+    }
+    if (fork) {
+      VATTN_CUDA(cudaStreamWaitEvent(main, side->join, 0));
+    } else if (decode && prefill) {
+      vattn_fwd_params_t d = *decode;
+      d.workspace = workspace ? static_cast<char*>(workspace) + a : nullptr;
+      d.workspace_bytes = workspace_bytes > a ? workspace_bytes - a : 0;
+      run_fwd(d, main);
     }
     return VATTN_OK;
   } catch (...) {

@@ -5,14 +5,16 @@
 // (sarathi/model_executor/parallel_utils/tensor_parallel/layers.py:432-461 -> mappings.py:16-26:
 // a cuBLAS GEMM, then NCCL).  Here it is ONE kernel per rank:
 //
-//   * CTA t owns hidden columns [128 t, 128 t + 128).  tcgen05: the weight rows are the MMA's M
-//     axis (W_o_shard is [hidden, K] K-major, exactly nn.Linear's layout), the tokens its N axis
-//     (<= 128, zero-filled to a multiple of 16 by TMA), the accumulator D^T[128 x tokens] lives in
-//     TMEM.  One TMA warp streams [128 x 64] weight atoms + the [tokens x 64] activation atom
-//     through a 4-stage ring, one thread issues the MMAs.
-//   * epilogue (4 warps = 128 TMEM lanes): accumulator -> bf16 -> shared memory (transposed back
-//     to [token][hidden]) -> 16-byte stores of the tile into EVERY rank's receive slot
-//     recv[parity][my_rank] over NVLink -> system fence -> per-tile flag on every rank;
+//   * CTA t owns hidden columns [n t, n t + n), n = 32 for hidden 4096 so that 128 CTAs stream the
+//     weight shard (HBM-bound: 2 K hidden bytes, ~1 FLOP/B per token row).  tcgen05: the tokens are
+//     the MMA's M axis (<= 128 rows, TMA loads only the real ones), the weight rows its N axis
+//     (W_o_shard is [hidden, K] K-major, exactly nn.Linear's layout), the accumulator
+//     D[tokens x n] lives in TMEM with lane = token.  One thread streams [n x 64] weight atoms and
+//     the [tokens x 64] activation atom (L2 resident) through a 6-stage TMA ring, one thread
+//     issues the MMAs.
+//   * epilogue (4 warps = 128 TMEM lanes = tokens): accumulator row -> bf16 -> 16-byte stores of
+//     the row segment into EVERY rank's receive slot recv[parity][my_rank] over NVLink -> system
+//     fence -> per-tile flag on every rank;
 //   * the same CTA then waits for the `world` flags of ITS tile, sums the `world` slots (local
 //     memory, fixed rank order so every rank gets bit-identical sums) and writes out[tokens, hidden].
 //   The tiles are independent, so the exchange of tile t overlaps the weight streaming of the
@@ -22,9 +24,9 @@
 // capturable; the receive slots and flags are double buffered on epoch parity.  Reuse is safe: a
 // rank writes parity e & 1 again in call e + 2, after its own call e + 1 finished, in which it
 // saw every peer's flag e + 1, which a peer only publishes after ITS call e (the last reader of
-// that parity) completed -- launches on one stream run in order.
-// Roofline: HBM (weights 2 K hidden bytes read once per rank; decode tokens <= 128 => ~1 FLOP/B
-// per token row); the exchange moves (world - 1) * tokens * hidden * 2 bytes per rank over NVLink.
+// that parity) completed -- launches on one stream run in order.  All CTAs of a call are
+// co-resident (grid <= 148, one CTA per SM), so waiting on a peer cannot starve a local tile.
+// The exchange moves (world - 1) * tokens * hidden * 2 bytes per rank over NVLink.
 #include <cuda.h>
 
 #include <type_traits>
@@ -40,10 +42,10 @@ namespace {
 using namespace ptx;
 
 constexpr int kMaxWorld = 8;
-constexpr int kTileH = 128;     // hidden columns per CTA (MMA M)
+constexpr int kMaxTileH = 128;  // hidden columns per CTA (MMA N): 32, 64 or 128
 constexpr int kKStep = 64;      // K elements per ring stage (one 128-byte swizzle atom)
-constexpr int kStages = 4;
-constexpr int kMaxTokens = 128;
+constexpr int kStages = 6;
+constexpr int kMaxTokens = 128; // MMA M
 constexpr int kThreads = 192;   // warps 0-3 epilogue, 4 TMA, 5 MMA
 constexpr uint32_t kSpinLimit = 1u << 24;  // ~20 s of polling before giving up on a peer
 
@@ -52,13 +54,13 @@ struct OprojParams {
   uint32_t* flags[kMaxWorld];  // rank r's flags: [2][n_tiles][kMaxWorld]
   char* out;                   // [tokens, hidden]
   uint32_t* epoch_state;       // [0] last completed epoch, [1] CTAs done, [2] error (spin limit hit)
-  int tokens, tokens_pad, hidden, k_steps, max_tokens, rank, world;
+  int tokens, tokens_pad, hidden, k_steps, max_tokens, rank, world, n_tile;
 };
 
 struct __align__(1024) OprojSmem {
-  uint8_t w[kStages][kTileH * 128];      // [128 rows x 128 B] SW128 atoms
-  uint8_t x[kStages][kMaxTokens * 128];  // [tokens_pad rows x 128 B]
-  uint8_t tile[kMaxTokens * kTileH * 2]; // epilogue staging [token][hidden] 16-bit
+  uint8_t x[kStages][kMaxTokens * 128];  // [128 rows x 128 B] SW128 atom; rows >= tokens_pad are never
+                                         // loaded and only feed accumulator lanes nobody reads
+  uint8_t w[kStages][kMaxTileH * 128];   // [n_tile rows x 128 B]
   uint64_t full[kStages], empty[kStages], acc_full;
   uint32_t tmem_base, epoch;
 };
@@ -96,7 +98,7 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
   OprojSmem& sm = *reinterpret_cast<OprojSmem*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
-  const uint32_t tmem_cols = p.tokens_pad <= 32 ? 32 : p.tokens_pad <= 64 ? 64 : 128;
+  const uint32_t tmem_cols = (uint32_t)p.n_tile;  // 32 / 64 / 128: a power of two >= 32
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) {
@@ -125,25 +127,25 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
   if (warp == 4) {
     // ---- TMA producer
     if (lane == 0) {
-      const uint32_t bytes = kTileH * 128 + p.tokens_pad * 128;
+      const uint32_t bytes = (uint32_t)(p.tokens_pad + p.n_tile) * 128;
       for (int k = 0; k < p.k_steps; k++) {
         const int s = k % kStages;
         if (k >= kStages) mbar_wait(&sm.empty[s], ((k / kStages) - 1) & 1);
         mbar_expect_tx(&sm.full[s], bytes);
-        tma_load_2d(sm.w[s], &w_map, &sm.full[s], k * kKStep, tile * kTileH);
+        tma_load_2d(sm.w[s], &w_map, &sm.full[s], k * kKStep, tile * p.n_tile);
         tma_load_2d(sm.x[s], &x_map, &sm.full[s], k * kKStep, 0);
       }
     }
   } else if (warp == 5) {
-    // ---- MMA issuer: D^T[128 hidden x tokens_pad] += W[128 x 64] . X[tokens_pad x 64]^T
+    // ---- MMA issuer: D[128 tokens x n_tile] += X[128 x 64] . W[n_tile x 64]^T
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(std::is_same<T, __half>::value ? kFmtF16 : kFmtBF16, kTileH,
-                                        (uint32_t)p.tokens_pad, 0, 0);
+      const uint32_t idesc = make_idesc(std::is_same<T, __half>::value ? kFmtF16 : kFmtBF16, kMaxTokens,
+                                        (uint32_t)p.n_tile, 0, 0);
       for (int k = 0; k < p.k_steps; k++) {
         const int s = k % kStages;
         mbar_wait(&sm.full[s], (k / kStages) & 1);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(sm.w[s]), b0 = smem_u32(sm.x[s]);
+        const uint32_t a0 = smem_u32(sm.x[s]), b0 = smem_u32(sm.w[s]);
 #pragma unroll
         for (int j = 0; j < kKStep / 16; j++)
           umma_ss(tmem, make_smem_desc(a0 + j * 32, 16, 1024, kLayoutSw128),
@@ -153,33 +155,39 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
       umma_commit(&sm.acc_full);
     }
   } else {
-    // ---- epilogue warps 0-3: TMEM lane = hidden column of the tile
+    // ---- epilogue warps 0-3: TMEM lane = token, columns = this tile's hidden columns
     const int t = threadIdx.x;  // 0..127
+    const bool live = t < p.tokens;
     mbar_wait(&sm.acc_full, 0);
     tc_fence_after();
-    T* stage = reinterpret_cast<T*>(sm.tile);
-    for (int c0 = 0; c0 < p.tokens_pad; c0 += 16) {
+    const size_t slot = (size_t)p.max_tokens * p.hidden * 2;
+    const size_t row_off = ((size_t)t * p.hidden + (size_t)tile * p.n_tile) * 2;  // this token's segment
+    const size_t my_slot = ((size_t)parity * p.world + p.rank) * slot;
+    // push: accumulator row -> 16-bit -> every rank's slot [parity][my rank]
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
       uint32_t r[16];
-      tmem_ld_x16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+      tmem_ld_x16(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);  // whole warp, also for dead lanes
       tmem_wait_ld();
+      if (live) {
+        uint4 v0, v1;
+        v0.x = Elem<T>::from_f2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+        v0.y = Elem<T>::from_f2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+        v0.z = Elem<T>::from_f2(__uint_as_float(r[4]), __uint_as_float(r[5]));
+        v0.w = Elem<T>::from_f2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+        v1.x = Elem<T>::from_f2(__uint_as_float(r[8]), __uint_as_float(r[9]));
+        v1.y = Elem<T>::from_f2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+        v1.z = Elem<T>::from_f2(__uint_as_float(r[12]), __uint_as_float(r[13]));
+        v1.w = Elem<T>::from_f2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+        const size_t off = my_slot + row_off + (size_t)c0 * 2;
 #pragma unroll
-      for (int j = 0; j < 16; j++)
-        if (c0 + j < p.tokens) stage[(c0 + j) * kTileH + t] = Elem<T>::from_f(__uint_as_float(r[j]));
+        for (int rk = 0; rk < kMaxWorld; rk++)
+          if (rk < p.world) {
+            st_sys_128(p.recv[rk] + off, v0);
+            st_sys_128(p.recv[rk] + off + 16, v1);
+          }
+      }
     }
     tc_fence_before();
-    named_bar_sync(1, 128);
-    // push the tile into every rank's slot [parity][my rank]
-    const int n_vec = p.tokens * (kTileH * 2 / 16);  // 16 vectors per token row of the tile
-    const size_t slot = (size_t)p.max_tokens * p.hidden * 2;
-    const size_t my_slot = ((size_t)parity * p.world + p.rank) * slot;
-    for (int v = t; v < n_vec; v += 128) {
-      const int tok = v >> 4, seg = v & 15;
-      const uint4 val = *reinterpret_cast<const uint4*>(sm.tile + (size_t)tok * (kTileH * 2) + seg * 16);
-      const size_t off = my_slot + ((size_t)tok * p.hidden + (size_t)tile * kTileH) * 2 + seg * 16;
-#pragma unroll
-      for (int r = 0; r < kMaxWorld; r++)
-        if (r < p.world) st_sys_128(p.recv[r] + off, val);
-    }
     __threadfence_system();
     named_bar_sync(1, 128);
     const size_t flag_row = ((size_t)parity * gridDim.x + tile) * kMaxWorld;
@@ -192,34 +200,34 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
           p.epoch_state[2] = 1;
           break;
         }
-        __nanosleep(64);
+        __nanosleep(32);
       }
     }
     named_bar_sync(1, 128);
     // reduce the `world` slots of this tile, rank order, fp32
-    const char* base = p.recv[p.rank] + (size_t)parity * p.world * slot;
-    for (int v = t; v < n_vec; v += 128) {
-      const int tok = v >> 4, seg = v & 15;
-      const size_t off = ((size_t)tok * p.hidden + (size_t)tile * kTileH) * 2 + seg * 16;
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const char* base = p.recv[p.rank] + (size_t)parity * p.world * slot + row_off;
+      for (int c0 = 0; c0 < p.n_tile; c0 += 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int r = 0; r < kMaxWorld; r++) {
-        if (r >= p.world) break;
-        const uint4 u = ld_sys_128(base + (size_t)r * slot + off);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        for (int rk = 0; rk < kMaxWorld; rk++) {
+          if (rk >= p.world) break;
+          const uint4 u = ld_sys_128(base + (size_t)rk * slot + (size_t)c0 * 2);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float2 f = Elem<T>::to_f2(w[j]);
-          acc[2 * j] += f.x;
-          acc[2 * j + 1] += f.y;
+          for (int j = 0; j < 4; j++) {
+            const float2 f = Elem<T>::to_f2(w[j]);
+            acc[2 * j] += f.x;
+            acc[2 * j + 1] += f.y;
+          }
         }
+        uint4 o;
+        o.x = Elem<T>::from_f2(acc[0], acc[1]);
+        o.y = Elem<T>::from_f2(acc[2], acc[3]);
+        o.z = Elem<T>::from_f2(acc[4], acc[5]);
+        o.w = Elem<T>::from_f2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(p.out + row_off + (size_t)c0 * 2) = o;
       }
-      uint4 o;
-      o.x = Elem<T>::from_f2(acc[0], acc[1]);
-      o.y = Elem<T>::from_f2(acc[2], acc[3]);
-      o.z = Elem<T>::from_f2(acc[4], acc[5]);
-      o.w = Elem<T>::from_f2(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(p.out + off) = o;
     }
   }
   __syncthreads();
@@ -247,7 +255,7 @@ size_t vattn_oproj_allreduce_recv_bytes(int32_t max_tokens, int32_t hidden, int3
   return (size_t)2 * world * max_tokens * hidden * 2;
 }
 size_t vattn_oproj_allreduce_flag_bytes(int32_t hidden) {
-  return (size_t)2 * (hidden / kTileH) * kMaxWorld * sizeof(uint32_t);
+  return (size_t)2 * (hidden / 32) * kMaxWorld * sizeof(uint32_t);  // sized for the smallest tile
 }
 
 int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, void* out, int32_t tokens,
@@ -264,8 +272,15 @@ int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, vo
     if (tokens <= 0 || tokens > kMaxTokens || tokens > max_tokens)
       throw UnsupportedError("[vattn] oproj_allreduce: 1..128 tokens per call (decode batches); larger "
                              "batches use the GEMM + all-reduce pair");
-    if (hidden % kTileH != 0 || hidden / kTileH > 148 || k_local % kKStep != 0 || k_local <= 0)
-      throw UnsupportedError("[vattn] oproj_allreduce: hidden must be a multiple of 128 (<= 18944) and "
+    // hidden columns per CTA: the smallest of 32 / 64 / 128 that keeps the grid co-resident
+    int n_tile = 0;
+    for (int n : {32, 64, 128})
+      if (hidden % n == 0 && hidden / n <= 148) {
+        n_tile = n;
+        break;
+      }
+    if (n_tile == 0 || k_local % kKStep != 0 || k_local <= 0)
+      throw UnsupportedError("[vattn] oproj_allreduce: hidden must be a multiple of 32 (<= 18944) and "
                              "the local K a multiple of 64");
     if (x_row_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
         (reinterpret_cast<uintptr_t>(out) & 15))
@@ -278,23 +293,24 @@ int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, vo
     p.out = static_cast<char*>(out);
     p.epoch_state = epoch_state;
     p.tokens = tokens;
-    p.tokens_pad = (tokens + 15) / 16 * 16;
+    p.tokens_pad = (tokens + 7) / 8 * 8;  // whole 8-row swizzle groups
+    p.n_tile = n_tile;
     p.hidden = hidden;
     p.k_steps = k_local / kKStep;
     p.max_tokens = max_tokens;
     p.rank = rank, p.world = world;
-    const CUtensorMap w_map = make_kmajor_map(w, hidden, k_local, (int64_t)k_local * 2, kTileH);
+    const CUtensorMap w_map = make_kmajor_map(w, hidden, k_local, (int64_t)k_local * 2, n_tile);
     const CUtensorMap x_map = make_kmajor_map(x, tokens, k_local, x_row_stride * 2, p.tokens_pad);
     const size_t smem = sizeof(OprojSmem) + 1024;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == VATTN_DTYPE_BF16) {
       VATTN_CUDA(cudaFuncSetAttribute(oproj_allreduce_kernel<__nv_bfloat16>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      oproj_allreduce_kernel<__nv_bfloat16><<<hidden / kTileH, kThreads, smem, s>>>(w_map, x_map, p);
+      oproj_allreduce_kernel<__nv_bfloat16><<<hidden / n_tile, kThreads, smem, s>>>(w_map, x_map, p);
     } else {
       VATTN_CUDA(cudaFuncSetAttribute(oproj_allreduce_kernel<__half>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      oproj_allreduce_kernel<__half><<<hidden / kTileH, kThreads, smem, s>>>(w_map, x_map, p);
+      oproj_allreduce_kernel<__half><<<hidden / n_tile, kThreads, smem, s>>>(w_map, x_map, p);
     }
     count_launch();
     VATTN_CUDA(cudaGetLastError());
