@@ -29,6 +29,7 @@
 // The exchange moves (world - 1) * tokens * hidden * 2 bytes per rank over NVLink.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "attn_common.cuh"
@@ -44,7 +45,8 @@ using namespace ptx;
 constexpr int kMaxWorld = 8;
 constexpr int kMaxTileH = 128;  // hidden columns per CTA (MMA N): 32, 64 or 128
 constexpr int kKStep = 64;      // K elements per ring stage (one 128-byte swizzle atom)
-constexpr int kStages = 6;
+constexpr int kMaxStages = 16;
+constexpr int kRingBytes = 192 * 1024;  // TMA ring; + 16 KB slack the 128-row A descriptor may read into
 constexpr int kMaxTokens = 128; // MMA M
 constexpr int kThreads = 192;   // warps 0-3 epilogue, 4 TMA, 5 MMA
 constexpr uint32_t kSpinLimit = 1u << 24;  // ~20 s of polling before giving up on a peer
@@ -54,14 +56,16 @@ struct OprojParams {
   uint32_t* flags[kMaxWorld];  // rank r's flags: [2][n_tiles][kMaxWorld]
   char* out;                   // [tokens, hidden]
   uint32_t* epoch_state;       // [0] last completed epoch, [1] CTAs done, [2] error (spin limit hit)
-  int tokens, tokens_pad, hidden, k_steps, max_tokens, rank, world, n_tile;
+  int tokens, tokens_pad, hidden, k_steps, max_tokens, rank, world, n_tile, k_rot, stages;
 };
 
+// Ring stage = [tokens_pad rows x 128 B] activation atom followed by [n_tile rows x 128 B] weight atom
+// (12 KB for 64 tokens x 32 columns => 16 stages in flight per CTA: the k loop is latency bound, so
+// depth is what buys bandwidth).  The MMA's A descriptor always spans 128 rows; rows >= tokens_pad
+// read whatever follows in the ring and only feed accumulator lanes nobody reads.
 struct __align__(1024) OprojSmem {
-  uint8_t x[kStages][kMaxTokens * 128];  // [128 rows x 128 B] SW128 atom; rows >= tokens_pad are never
-                                         // loaded and only feed accumulator lanes nobody reads
-  uint8_t w[kStages][kMaxTileH * 128];   // [n_tile rows x 128 B]
-  uint64_t full[kStages], empty[kStages], acc_full;
+  uint8_t ring[kRingBytes + kMaxTokens * 128];
+  uint64_t full[kMaxStages], empty[kMaxStages], acc_full;
   uint32_t tmem_base, epoch;
 };
 
@@ -101,7 +105,7 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
   const uint32_t tmem_cols = (uint32_t)p.n_tile;  // 32 / 64 / 128: a power of two >= 32
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; s++) {
+    for (int s = 0; s < p.stages; s++) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
@@ -123,17 +127,23 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
   const uint32_t tmem = sm.tmem_base;
   const uint32_t epoch = sm.epoch;
   const int parity = epoch & 1;
+  const uint32_t x_bytes = (uint32_t)p.tokens_pad * 128, stage_bytes = x_bytes + (uint32_t)p.n_tile * 128;
 
   if (warp == 4) {
     // ---- TMA producer
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(p.tokens_pad + p.n_tile) * 128;
+      // every CTA needs the same [tokens x 64] activation atom at step k: start each tile at a
+      // different k so the 128 CTAs do not hammer one L2 line set at the same moment
+      const int k_first = (int)(((long long)tile * p.k_rot) % p.k_steps);
       for (int k = 0; k < p.k_steps; k++) {
-        const int s = k % kStages;
-        if (k >= kStages) mbar_wait(&sm.empty[s], ((k / kStages) - 1) & 1);
-        mbar_expect_tx(&sm.full[s], bytes);
-        tma_load_2d(sm.w[s], &w_map, &sm.full[s], k * kKStep, tile * p.n_tile);
-        tma_load_2d(sm.x[s], &x_map, &sm.full[s], k * kKStep, 0);
+        const int s = k % p.stages;
+        int kk = k + k_first;
+        if (kk >= p.k_steps) kk -= p.k_steps;
+        if (k >= p.stages) mbar_wait(&sm.empty[s], ((k / p.stages) - 1) & 1);
+        mbar_expect_tx(&sm.full[s], stage_bytes);
+        uint8_t* st = sm.ring + (size_t)s * stage_bytes;
+        tma_load_2d(st, &x_map, &sm.full[s], kk * kKStep, 0);
+        tma_load_2d(st + x_bytes, &w_map, &sm.full[s], kk * kKStep, tile * p.n_tile);
       }
     }
   } else if (warp == 5) {
@@ -142,10 +152,10 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
       const uint32_t idesc = make_idesc(std::is_same<T, __half>::value ? kFmtF16 : kFmtBF16, kMaxTokens,
                                         (uint32_t)p.n_tile, 0, 0);
       for (int k = 0; k < p.k_steps; k++) {
-        const int s = k % kStages;
-        mbar_wait(&sm.full[s], (k / kStages) & 1);
+        const int s = k % p.stages;
+        mbar_wait(&sm.full[s], (k / p.stages) & 1);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(sm.x[s]), b0 = smem_u32(sm.w[s]);
+        const uint32_t a0 = smem_u32(sm.ring) + (uint32_t)s * stage_bytes, b0 = a0 + x_bytes;
 #pragma unroll
         for (int j = 0; j < kKStep / 16; j++)
           umma_ss(tmem, make_smem_desc(a0 + j * 32, 16, 1024, kLayoutSw128),
@@ -274,8 +284,10 @@ int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, vo
                              "batches use the GEMM + all-reduce pair");
     // hidden columns per CTA: the smallest of 32 / 64 / 128 that keeps the grid co-resident
     int n_tile = 0;
+    static const int forced_tile = std::getenv("VATTN_OPROJ_NTILE") ? std::atoi(std::getenv("VATTN_OPROJ_NTILE")) : 0;
+    static const int k_rot = std::getenv("VATTN_OPROJ_KROT") ? std::atoi(std::getenv("VATTN_OPROJ_KROT")) : 5;
     for (int n : {32, 64, 128})
-      if (hidden % n == 0 && hidden / n <= 148) {
+      if (hidden % n == 0 && hidden / n <= 148 && n >= forced_tile) {
         n_tile = n;
         break;
       }
@@ -295,6 +307,10 @@ int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, vo
     p.tokens = tokens;
     p.tokens_pad = (tokens + 7) / 8 * 8;  // whole 8-row swizzle groups
     p.n_tile = n_tile;
+    p.k_rot = k_rot;
+    p.stages = kRingBytes / ((p.tokens_pad + n_tile) * 128);
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    if (p.stages > p.k_steps) p.stages = p.k_steps;
     p.hidden = hidden;
     p.k_steps = k_local / kKStep;
     p.max_tokens = max_tokens;
