@@ -297,7 +297,7 @@ int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, vo
     if (x_row_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
         (reinterpret_cast<uintptr_t>(out) & 15))
       throw ArgError("[vattn] oproj_allreduce: tensors must be 16-byte aligned");
-    OprojParams p;
+    OprojParams p{};
     for (int r = 0; r < kMaxWorld; r++) {
       p.recv[r] = r < world ? reinterpret_cast<char*>(peer_recv_ptrs[r]) : nullptr;
       p.flags[r] = r < world ? reinterpret_cast<uint32_t*>(peer_flag_ptrs[r]) : nullptr;
@@ -308,11 +308,11 @@ int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, vo
     p.tokens_pad = (tokens + 7) / 8 * 8;  // whole 8-row swizzle groups
     p.n_tile = n_tile;
     p.k_rot = k_rot;
+    p.hidden = hidden;
+    p.k_steps = k_local / kKStep;
     p.stages = kRingBytes / ((p.tokens_pad + n_tile) * 128);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (p.stages > p.k_steps) p.stages = p.k_steps;
-    p.hidden = hidden;
-    p.k_steps = k_local / kKStep;
     p.max_tokens = max_tokens;
     p.rank = rank, p.world = world;
     const CUtensorMap w_map = make_kmajor_map(w, hidden, k_local, (int64_t)k_local * 2, n_tile);
