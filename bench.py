@@ -503,7 +503,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "fa_vattn"])
     ap.add_argument("--resident-layers", type=int, default=4)
-    ap.add_argument("--tp-collective", default="peer", choices=["fused", "peer", "nccl"])
+    # N > 1 default: cuBLAS GEMM + NCCL inside the CUDA graph -- the fastest measured arrangement at N = 2
+    # (profiles/r1_tp2_collective_arms.md); "fused" is our single GEMM + all-reduce kernel, "peer" our
+    # one-shot all-reduce kernel (eager only: its epoch is a host-side argument)
+    ap.add_argument("--tp-collective", default="nccl", choices=["fused", "peer", "nccl"])
     ap.add_argument("--no-tp-graph", dest="tp_graph", action="store_false",
                     help="N > 1: launch the 32 layer-calls eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
