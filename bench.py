@@ -163,11 +163,28 @@ def run_ours(args):
     tp_attn = None
     if world > 1:
         # the o_proj all-reduce: our one-shot kernel over NVLink peer memory (default) or NCCL
+        def all_ranks_ok(ok: bool) -> bool:
+            t = torch.tensor([0 if ok else 1], device=dev, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return int(t.item()) == 0
+
         if args.tp_collective == "fused":
-            tp_attn = HeadShardedAttentionFused(shard, w_o, att.flash_attn_with_kvcache, max_tokens=BATCH)
-        elif args.tp_collective == "peer":
+            # our GEMM + all-reduce kernel; probed once (symmetric-memory rendezvous, one exchange) and
+            # replaced by the cuBLAS + NCCL pair on EVERY rank if any rank could not bring it up
+            ok = True
+            try:
+                tp_attn = HeadShardedAttentionFused(shard, w_o, att.flash_attn_with_kvcache, max_tokens=BATCH)
+                tp_attn.op(torch.zeros(BATCH, hq * D, device=dev, dtype=DTYPE))
+                torch.cuda.synchronize(dev)
+                ok = not tp_attn.op.failed()
+            except Exception as e:                       # noqa: BLE001 -- any failure means "fall back"
+                print(f"[bench] rank {rank}: fused o_proj + all-reduce unavailable: {e}", file=sys.stderr)
+                ok = False
+            if not all_ranks_ok(ok):
+                args.tp_collective = "nccl"
+        if args.tp_collective == "peer":
             tp_attn = HeadShardedAttentionPeer(shard, w_o, att.flash_attn_with_kvcache, max_tokens=BATCH)
-        else:
+        elif args.tp_collective == "nccl":
             tp_attn = HeadShardedAttention(shard, w_o, att.flash_attn_with_kvcache)
     scale = D ** -0.5
     sink = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -503,10 +520,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "fa_vattn"])
     ap.add_argument("--resident-layers", type=int, default=4)
-    # N > 1 default: cuBLAS GEMM + NCCL inside the CUDA graph -- the fastest measured arrangement at N = 2
-    # (profiles/r1_tp2_collective_arms.md); "fused" is our single GEMM + all-reduce kernel, "peer" our
-    # one-shot all-reduce kernel (eager only: its epoch is a host-side argument)
-    ap.add_argument("--tp-collective", default="nccl", choices=["fused", "peer", "nccl"])
+    # N > 1: "fused" = our single GEMM + all-reduce kernel (csrc/oproj_allreduce.cu) inside the CUDA graph:
+    # 5669 vs 5443 tokens/s for cuBLAS + NCCL at N = 4, 3060 vs 3103 at N = 2 (profiles/); "peer" = cuBLAS +
+    # our one-shot all-reduce kernel (eager only: its epoch is a host-side argument); "nccl" = cuBLAS + NCCL
+    ap.add_argument("--tp-collective", default="fused", choices=["fused", "peer", "nccl"])
     ap.add_argument("--no-tp-graph", dest="tp_graph", action="store_false",
                     help="N > 1: launch the 32 layer-calls eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
