@@ -40,3 +40,36 @@ def test_no_cpu_fallback_for_cuda_backend():
     rc = _lib.lib.vattn_create(ctypes.byref(h), _lib.BACKEND_CUDA)
     assert rc < 0
     assert "libcuda" in _lib.last_error() or "driver" in _lib.last_error().lower()
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_binding(repo_root, tmp_path):
+    """include/vattn_b200.h compiles as C11 (no C++, no torch types) and every struct the ctypes
+    binding mirrors has the same size and field offsets as the compiler gives the header's."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    structs = {"vattn_fwd_params_t": _lib.FwdParams, "vattn_config_t": _lib.VattnConfig,
+               "vattn_step_stats_t": _lib.StepStats}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "vattn_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-pedantic", f"-I{repo_root / 'include'}", str(src),
+                    "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        s, f, v = ln.split()
+        got[(s, f)] = int(v)
+    for cname, cls in structs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
