@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/validate.log) 2>&1
-echo "=== pytest -m gpu"; timeout 1800 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -15
+echo "=== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q --timeout 90 2>&1 | tail -15
 echo "=== smoke"; timeout 300 python __graft_entry__.py smoke
 echo "=== bench (ours)"; timeout 900 python bench.py | tee gpurun_out/bench_ours.json
 if [ "${1:-}" = "full" ]; then
