@@ -20,8 +20,11 @@ roofline  dominant kernel = the decode attention sweep; algorithmic bytes per la
         timed region (vattn_kernel_timing), against the measured HBM copy bandwidth.
 N > 1   head-sharded tensor parallel: rank r owns Hq/N q heads and Hkv/N kv heads and
         its own allocator; per layer-call the rank multiplies its attention output with its
-        o_proj shard and ONE NCCL all-reduce sums the [64, 4096] partials.  The model is fixed,
-        so per-GPU work shrinks with N: "scaling": "strong".
+        o_proj shard and ONE all-reduce sums the [64, 4096] partials -- by default both in our
+        fused kernel (--tp-collective fused|peer|nccl), the 32 layer-calls replayed from a CUDA graph
+        (the roofline's kernel time then comes from K eager iterations right after the timed
+        region: events cannot be read back from inside a graph).  The model is fixed, so per-GPU
+        work shrinks with N: "scaling": "strong".
 --impl reference   the reference's CPU path for the same metric: torch SDPA over the same shapes
         on the host cores (oracle/attention_ref.sdpa_decode_cpu), a bounded sample per step.
 --impl fa_vattn    (not run by the driver) flash_attn.flash_attn_with_kvcache over the same
@@ -162,7 +165,7 @@ def run_ours(args):
     w_o = (torch.randn(hq * D, HIDDEN, device=dev, generator=g) * 0.02).to(DTYPE) if world > 1 else None
     tp_attn = None
     if world > 1:
-        # the o_proj all-reduce: our one-shot kernel over NVLink peer memory (default) or NCCL
+        # the o_proj GEMM + all-reduce arrangement (--tp-collective)
         def all_ranks_ok(ok: bool) -> bool:
             t = torch.tensor([0 if ok else 1], device=dev, dtype=torch.int32)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
