@@ -91,9 +91,9 @@ int tiles_per_chunk_for(const vattn_fwd_params_t& p) {
   static const int forced = env_int("VATTN_DECODE_TPC", 0);
   const int64_t slots = 148 * 2;
   int64_t tpc = total / slots;
-  if (forced > 0) tpc = forced;
   if (tpc < 1) tpc = 1;
   if (tpc > kMaxTilesPerChunk) tpc = kMaxTilesPerChunk;
+  if (forced > 0) tpc = forced;  // experiments may exceed the cap (the kernel loops over any count)
   return (int)tpc;
 }
 
