@@ -346,3 +346,20 @@ def test_cleanup_releases_everything(mock_backend):
     va.init_kvcache(1, 1, 64, 1, 16384, 0, torch.float16, 2 * MB, False)
     log = va.get_driver_log()
     assert [r[0] for r in log].count(1) == 2
+
+
+def test_logical_pages_cleanup_balances_the_driver(mock_backend):
+    """256 KB logical pages: after cleanup every chunk that was created is released, every chunk
+    that was mapped is unmapped, every reservation freed (driver log of the mock)."""
+    page = 256 * 1024
+    model, _ = make_pair(2, 2, 64, 4, 32768, mem_pages=64, page=page)
+    tpp = model.tokens_per_page
+    va.step([5 * tpp + 3, tpp, 0, 9 * tpp], True)
+    va.step([5 * tpp + 3, 0, 17, 9 * tpp], True)
+    va.cleanup()
+    log = va.get_driver_log()
+    n = lambda op: sum(1 for r in log if r[0] == op)
+    assert n(2) > 0 and n(2) == n(6)          # create == release
+    assert n(3) > 0 and n(3) == n(5)          # map == unmap
+    assert n(1) == n(7) == 4                   # reserve == addr_free (2 layers x K, V)
+    va.init_kvcache(1, 1, 64, 1, 16384, 0, torch.float16, 2 * MB, False)   # leave a live config for the fixture

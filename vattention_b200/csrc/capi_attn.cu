@@ -399,6 +399,9 @@ static int fwd_kvcache_host_impl(const vattn_fwd_params_t* hp, void* stream_, bo
   if (!hp) return VATTN_ERR_INVALID;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   try {
+    if (hp->rotary_cos || hp->rotary_sin)
+      throw UnsupportedError("[vattn] the host-buffer entry point takes no rotary tables (device-resident "
+                             "cos/sin go through vattn_fwd_kvcache)");
     std::lock_guard<std::mutex> g(g_stage.mu);
     const size_t eb = 2;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
