@@ -282,7 +282,7 @@ if __name__ == "__main__":
     ap.add_argument("what", choices=["prefill", "pod", "alloc", "decode"])
     ap.add_argument("--impl", default="ours", choices=["ours", "fa", "fi"])
     ap.add_argument("--chunk", type=int, default=2048)
-    ap.add_argument("--ctx", type=int, default=131072)
+    ap.add_argument("--ctx", type=int, default=None, help="context length (prefill: 131072, decode: 32768)")
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--prefills", type=int, default=8)
     ap.add_argument("--prefill-len", type=int, default=16384)
@@ -298,4 +298,6 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--calls", type=int, default=20)
     a = ap.parse_args()
+    if a.ctx is None:
+        a.ctx = 32768 if a.what == "decode" else 131072
     {"prefill": prefill, "pod": pod, "alloc": alloc, "decode": decode}[a.what](a)
