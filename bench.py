@@ -314,6 +314,10 @@ def run_ours(args):
         outh = torch.empty(BATCH, 1, hq, D, dtype=DTYPE).pin_memory()
         sl_h = torch.empty(BATCH, dtype=torch.int32).pin_memory()
         pin_partial = torch.empty(BATCH, HIDDEN, dtype=DTYPE).pin_memory() if world > 1 else None
+        # VATTN_E2E_PIPELINED=1: copies on their own streams (vattn_fwd_kvcache_host_pipelined); not the
+        # default until it has been measured on the GPU
+        e2e_pipelined = world == 1 and os.environ.get("VATTN_E2E_PIPELINED", "0") == "1"
+        outh_l = [outh, torch.empty_like(outh).pin_memory()]
 
         def one_step_e2e(lens_now):
             new_lens = [n + 1 for n in lens_now]
@@ -327,7 +331,9 @@ def run_ours(args):
                     # enqueue only; one stream synchronisation per decode iteration (below) delivers
                     # the result of the last layer to the host
                     att.flash_attn_with_kvcache_host(qh[layer], kc, vc, knh[layer], vnh[layer], sl_h, idx_h,
-                                                     outh, softmax_scale=scale, causal=True, wait=False)
+                                                     outh_l[layer & 1] if e2e_pipelined else outh,
+                                                     softmax_scale=scale, causal=True, wait=False,
+                                                     pipelined=e2e_pipelined)
                 else:
                     qd = qh[layer].to(dev, non_blocking=True)
                     knd, vnd = knh[layer].to(dev, non_blocking=True), vnh[layer].to(dev, non_blocking=True)
@@ -335,6 +341,8 @@ def run_ours(args):
                     part = tp_attn.forward(qd, kc, vc, knd, vnd, cache_seqlens=sld, cache_batch_idx=idd,
                                            softmax_scale=scale, causal=True)
                     pin_partial.copy_(part, non_blocking=True)
+            if e2e_pipelined and world == 1:
+                att.host_pipeline_join(dev)
             torch.cuda.current_stream(dev).synchronize()
             return new_lens
 
@@ -356,7 +364,8 @@ def run_ours(args):
         e2e = {"value": round(BATCH * K / (ms_e / 1e3), 2), "unit": "tokens/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": round(ms_e / K, 3),
-               "api": "vattn_fwd_kvcache_host_async x32 + one stream sync per step (C ABI, pinned host q/k/v/idx/out)" if world == 1
+               "api": ("vattn_fwd_kvcache_host_pipelined x32 + join + one stream sync per step" if e2e_pipelined else
+                       "vattn_fwd_kvcache_host_async x32 + one stream sync per step (C ABI, pinned host q/k/v/idx/out)") if world == 1
                else "pinned host -> HeadShardedAttention.forward -> pinned host"}
 
     # ---- CPU baseline (rank 0, N == 1) ---------------------------------------------------

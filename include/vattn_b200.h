@@ -263,6 +263,13 @@ int vattn_fwd_kvcache_host(const vattn_fwd_params_t* p, void* stream);
  * must stay untouched until the stream is drained.                                            */
 int vattn_fwd_kvcache_host_async(const vattn_fwd_params_t* p, void* stream);
 
+/* Pipelined variant: the host->device copies of call i+1 and the device->host copy of call i-1
+ * overlap the kernels of call i (own copy streams, two staging slots).  `stream` alone no longer
+ * covers the output copies: call vattn_host_pipeline_join(stream) once before synchronising it
+ * (e.g. once per decode iteration); host buffers must stay untouched until then.               */
+int vattn_fwd_kvcache_host_pipelined(const vattn_fwd_params_t* p, void* stream);
+int vattn_host_pipeline_join(void* stream);
+
 /* One-shot all-reduce(sum) over NVLink peer memory for the head-sharded attention block: the
  * only collective on the path (the o_proj output all-reduce, tensor_parallel/layers.py:448-451 ->
  * mappings.py:16-26, NCCL in the reference).  peer_partial_ptrs[r] / peer_flag_ptrs[r] are the

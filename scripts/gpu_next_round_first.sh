@@ -14,6 +14,9 @@ if [ "${1:-}" = "n8" ]; then
   echo "=== bench nccl + graph"; timeout 300 $TR --master-port 29633 bench.py --gpus 8 --no-e2e --tp-collective nccl 2>&1 | grep '^{' | tee gpurun_out/bench_tp8_nccl_graph.json
   exit 0
 fi
+echo "=== host-buffer entry points: parity (incl. the opt-in pipelined variant), then e2e with it"
+VATTN_TEST_PIPELINED=1 timeout 200 python -m pytest tests/test_zz_gpu_host_path.py -q --timeout 60 2>&1 | tail -5
+VATTN_E2E_PIPELINED=1 timeout 400 python bench.py --no-cpu | tee gpurun_out/bench_e2e_pipelined.json
 echo "=== headline decode: tiles per chunk beyond the cap of 16 (model: 32..64 may save a few % of waves)"
 for t in 0 16 32 64 128; do echo "tpc=$t"; VATTN_DECODE_TPC=$t $B decode --ctx 32768; done
 echo "=== fused o_proj kernel, world 1, dense ring"; timeout 120 python scripts/debug/oproj_latency.py

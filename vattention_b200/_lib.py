@@ -120,6 +120,8 @@ _SIGS = {
                                    C.c_int32, C.c_void_p]),
     "vattn_fwd_kvcache_host": (C.c_int, [_P(FwdParams), C.c_void_p]),
     "vattn_fwd_kvcache_host_async": (C.c_int, [_P(FwdParams), C.c_void_p]),
+    "vattn_fwd_kvcache_host_pipelined": (C.c_int, [_P(FwdParams), C.c_void_p]),
+    "vattn_host_pipeline_join": (C.c_int, [C.c_void_p]),
     "vattn_allreduce_oneshot": (C.c_int, [_P(C.c_uint64), _P(C.c_uint64), C.c_void_p, C.c_int64, C.c_int,
                                           C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
     "vattn_oproj_allreduce_recv_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),

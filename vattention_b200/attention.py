@@ -294,12 +294,16 @@ def flash_attn_with_kvcache_host(q_host: torch.Tensor, k_cache: torch.Tensor, v_
                                  cache_seqlens_host: Optional[torch.Tensor],
                                  cache_batch_idx_host: Optional[torch.Tensor], out_host: torch.Tensor,
                                  softmax_scale: Optional[float] = None, causal: bool = False,
-                                 impl: str = "auto", wait: bool = True) -> torch.Tensor:
+                                 impl: str = "auto", wait: bool = True,
+                                 pipelined: bool = False) -> torch.Tensor:
     """Same operation with HOST (ideally pinned) q / k / v / index / out buffers and device-resident
     caches: the library copies in, runs the kernels and copies the result back, then drains the
     stream (vattn_fwd_kvcache_host).  wait=False enqueues only (vattn_fwd_kvcache_host_async): the
     result is valid after the stream is synchronised, and the layers of one decode iteration can be
-    issued back to back.  This is the call bench.py's `e2e` leg times."""
+    issued back to back.  This is the call bench.py's `e2e` leg times.
+    pipelined=True (with wait=False) moves the copies to their own streams so they overlap the
+    neighbouring calls' kernels (vattn_fwd_kvcache_host_pipelined); call host_pipeline_join() before
+    synchronising the stream."""
     for t in (q_host, k_host, v_host, cache_seqlens_host, cache_batch_idx_host, out_host):
         if t is not None and (t.is_cuda or not t.is_contiguous()):
             raise RuntimeError("host tensors must be contiguous CPU tensors")
@@ -307,9 +311,17 @@ def flash_attn_with_kvcache_host(q_host: torch.Tensor, k_cache: torch.Tensor, v_
         softmax_scale = q_host.shape[-1] ** (-0.5)
     p = _fill_params(q_host, k_cache, v_cache, k_host, v_host, out_host, cache_seqlens_host,
                      cache_batch_idx_host, softmax_scale, causal, impl, 0, None)
-    fn = lib.vattn_fwd_kvcache_host if wait else lib.vattn_fwd_kvcache_host_async
+    if pipelined and wait:
+        raise RuntimeError("pipelined=True needs wait=False (join with host_pipeline_join())")
+    fn = lib.vattn_fwd_kvcache_host if wait else (
+        lib.vattn_fwd_kvcache_host_pipelined if pipelined else lib.vattn_fwd_kvcache_host_async)
     check(fn(C.byref(p), _stream(k_cache.device)))
     return out_host
+
+
+def host_pipeline_join(device: torch.device) -> None:
+    """Make the current stream wait for every output copy of pipelined host calls still in flight."""
+    check(lib.vattn_host_pipeline_join(_stream(device)))
 
 
 def kernel_timing(op: int):

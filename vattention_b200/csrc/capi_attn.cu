@@ -466,6 +466,138 @@ int vattn_fwd_kvcache_host_async(const vattn_fwd_params_t* hp, void* stream) {
   return fwd_kvcache_host_impl(hp, stream, false);
 }
 
+// ---- pipelined host-buffer entry point ---------------------------------------------------------
+// Same contract as vattn_fwd_kvcache_host_async, but the copies leave the compute stream: inputs of
+// call i+1 travel host->device on a copy-in stream while the kernels of call i run, outputs travel
+// device->host on a copy-out stream while the kernels of call i+1 run (two staging slots, events
+// between the three streams).  The caller's stream therefore does NOT cover the last copies:
+// vattn_host_pipeline_join(stream) makes it wait for every output still in flight -- call it once
+// before synchronising (e.g. once per decode iteration).
+namespace {
+struct HostPipe {
+  cudaStream_t in = nullptr, out = nullptr;
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  void* dev[2] = {nullptr, nullptr};
+  size_t cap[2] = {0, 0};
+  void* ws = nullptr;
+  size_t ws_cap = 0;
+  uint64_t calls = 0;
+};
+std::mutex g_pipe_mu;
+std::unordered_map<cudaStream_t, HostPipe> g_pipes;
+
+HostPipe& pipe_for(cudaStream_t main) {
+  HostPipe& hp = g_pipes[main];
+  if (!hp.in) {
+    VATTN_CUDA(cudaStreamCreateWithFlags(&hp.in, cudaStreamNonBlocking));
+    VATTN_CUDA(cudaStreamCreateWithFlags(&hp.out, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; s++) {
+      VATTN_CUDA(cudaEventCreateWithFlags(&hp.h2d_done[s], cudaEventDisableTiming));
+      VATTN_CUDA(cudaEventCreateWithFlags(&hp.kernel_done[s], cudaEventDisableTiming));
+      VATTN_CUDA(cudaEventCreateWithFlags(&hp.d2h_done[s], cudaEventDisableTiming));
+    }
+  }
+  return hp;
+}
+void grow(void** ptr, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return;
+  if (*ptr) VATTN_CUDA(cudaFree(*ptr));  // synchronises the device: nothing is using the old block after this
+  *ptr = nullptr, *cap = 0;
+  VATTN_CUDA(cudaMalloc(ptr, bytes));
+  *cap = bytes;
+}
+}  // namespace
+
+int vattn_fwd_kvcache_host_pipelined(const vattn_fwd_params_t* hp, void* stream_) {
+  if (!hp) return VATTN_ERR_INVALID;
+  cudaStream_t main = static_cast<cudaStream_t>(stream_);
+  try {
+    if (hp->rotary_cos || hp->rotary_sin)
+      throw UnsupportedError("[vattn] the host-buffer entry points take no rotary tables");
+    std::lock_guard<std::mutex> g(g_pipe_mu);
+    HostPipe& pp = pipe_for(main);
+    const int s = (int)(pp.calls & 1);
+    const size_t eb = 2;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t q_bytes = (size_t)hp->batch * hp->seqlen_q * hp->num_heads * hp->head_dim * eb;
+    const size_t kn_bytes =
+        hp->k_new ? (size_t)hp->batch * hp->seqlen_new * hp->num_kv_heads * hp->head_dim * eb : 0;
+    const size_t idx_bytes = (size_t)hp->batch * sizeof(int32_t);
+    grow(&pp.dev[s], &pp.cap[s], up(q_bytes) * 2 + up(kn_bytes) * 2 + up(idx_bytes) * 2);
+    char* d_q = static_cast<char*>(pp.dev[s]);
+    char* d_o = d_q + up(q_bytes);
+    char* d_kn = d_o + up(q_bytes);
+    char* d_vn = d_kn + up(kn_bytes);
+    char* d_sl = d_vn + up(kn_bytes);
+    char* d_bi = d_sl + up(idx_bytes);
+
+    // inputs: slot s was last read by the kernels of call i-2
+    if (pp.used[s]) VATTN_CUDA(cudaStreamWaitEvent(pp.in, pp.kernel_done[s], 0));
+    vattn_fwd_params_t p = *hp;
+    VATTN_CUDA(cudaMemcpyAsync(d_q, hp->q, q_bytes, cudaMemcpyHostToDevice, pp.in));
+    p.q = d_q;
+    p.q_head_stride = hp->head_dim;
+    p.q_row_stride = (int64_t)hp->num_heads * hp->head_dim;
+    p.q_batch_stride = p.q_row_stride * hp->seqlen_q;
+    p.out = d_o;
+    p.o_head_stride = p.q_head_stride, p.o_row_stride = p.q_row_stride, p.o_batch_stride = p.q_batch_stride;
+    if (hp->k_new) {
+      VATTN_CUDA(cudaMemcpyAsync(d_kn, hp->k_new, kn_bytes, cudaMemcpyHostToDevice, pp.in));
+      VATTN_CUDA(cudaMemcpyAsync(d_vn, hp->v_new, kn_bytes, cudaMemcpyHostToDevice, pp.in));
+      p.k_new = d_kn, p.v_new = d_vn;
+      p.knew_head_stride = p.vnew_head_stride = hp->head_dim;
+      p.knew_row_stride = p.vnew_row_stride = (int64_t)hp->num_kv_heads * hp->head_dim;
+      p.knew_batch_stride = p.vnew_batch_stride = p.knew_row_stride * hp->seqlen_new;
+    }
+    if (hp->cache_seqlens) {
+      VATTN_CUDA(cudaMemcpyAsync(d_sl, hp->cache_seqlens, idx_bytes, cudaMemcpyHostToDevice, pp.in));
+      p.cache_seqlens = reinterpret_cast<const int32_t*>(d_sl);
+    }
+    if (hp->cache_batch_idx) {
+      VATTN_CUDA(cudaMemcpyAsync(d_bi, hp->cache_batch_idx, idx_bytes, cudaMemcpyHostToDevice, pp.in));
+      p.cache_batch_idx = reinterpret_cast<const int32_t*>(d_bi);
+    }
+    VATTN_CUDA(cudaEventRecord(pp.h2d_done[s], pp.in));
+    p.softmax_lse = nullptr;
+    validate(p);
+    const size_t need = p.batch ? workspace_for(p, choose(p)) : 0;
+    if (need) grow(&pp.ws, &pp.ws_cap, need);  // one workspace: the kernels of successive calls are stream ordered
+    p.workspace = pp.ws;
+    p.workspace_bytes = pp.ws_cap;
+
+    // kernels: after this call's inputs landed and after the output staging of call i-2 was read out
+    VATTN_CUDA(cudaStreamWaitEvent(main, pp.h2d_done[s], 0));
+    if (pp.used[s]) VATTN_CUDA(cudaStreamWaitEvent(main, pp.d2h_done[s], 0));
+    run_fwd(p, main);
+    VATTN_CUDA(cudaEventRecord(pp.kernel_done[s], main));
+
+    // output: device -> host on the copy-out stream
+    VATTN_CUDA(cudaStreamWaitEvent(pp.out, pp.kernel_done[s], 0));
+    VATTN_CUDA(cudaMemcpyAsync(hp->out, d_o, q_bytes, cudaMemcpyDeviceToHost, pp.out));
+    VATTN_CUDA(cudaEventRecord(pp.d2h_done[s], pp.out));
+    pp.used[s] = true;
+    pp.calls++;
+    return VATTN_OK;
+  } catch (...) {
+    return translate_attn_exception();
+  }
+}
+
+int vattn_host_pipeline_join(void* stream_) {
+  cudaStream_t main = static_cast<cudaStream_t>(stream_);
+  try {
+    std::lock_guard<std::mutex> g(g_pipe_mu);
+    auto it = g_pipes.find(main);
+    if (it == g_pipes.end()) return VATTN_OK;
+    for (int s = 0; s < 2; s++)
+      if (it->second.used[s]) VATTN_CUDA(cudaStreamWaitEvent(main, it->second.d2h_done[s], 0));
+    return VATTN_OK;
+  } catch (...) {
+    return translate_attn_exception();
+  }
+}
+
 uint64_t vattn_launch_count(void) { return g_launch_count.load(); }
 
 int vattn_kernel_timing(int op, double* total_ms, uint64_t* launches) {
