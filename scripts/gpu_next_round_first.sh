@@ -14,6 +14,12 @@ if [ "${1:-}" = "n8" ]; then
   echo "=== bench nccl + graph"; timeout 300 $TR --master-port 29633 bench.py --gpus 8 --no-e2e --tp-collective nccl 2>&1 | grep '^{' | tee gpurun_out/bench_tp8_nccl_graph.json
   exit 0
 fi
+echo "=== prefill with the S row held in registers (setmaxnreg 56 / 224): parity, then throughput vs the default"
+VATTN_PREFILL_REGS=1 timeout 300 python -m pytest tests/test_gpu_attention.py -q --timeout 60 -k "prefill or pod or masked or lse" 2>&1 | tail -4
+for c in 512 2048 8192; do
+  timeout 300 python scripts/bench_extra.py prefill --chunk $c
+  VATTN_PREFILL_REGS=1 timeout 300 python scripts/bench_extra.py prefill --chunk $c
+done
 echo "=== host-buffer entry points: parity (incl. the opt-in pipelined variant), then e2e with it"
 VATTN_TEST_PIPELINED=1 timeout 200 python -m pytest tests/test_zz_gpu_host_path.py -q --timeout 60 2>&1 | tail -5
 VATTN_E2E_PIPELINED=1 timeout 400 python bench.py --no-cpu | tee gpurun_out/bench_e2e_pipelined.json

@@ -76,7 +76,7 @@ struct __align__(1024) Prefill2KernelSmem {
 };
 
 // two 128-row blocks per CTA with one softmax warpgroup each (prefill2_work)
-template <typename T>
+template <typename T, bool REGS>
 __global__ void __launch_bounds__(kPrefill2Threads, 1)
 prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                    const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap kmap_tail,
@@ -99,8 +99,10 @@ prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
   const int pairs = (p.num_m_tiles + 1) / 2;
-  prefill2_work<T>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem,
-                   pairs - 1 - blockIdx.x, blockIdx.y, blockIdx.z, false);
+  // REGS: 384 threads x 168 registers at launch; inside prefill2_work the producer / MMA warpgroup
+  // drops to 56 and the two softmax warpgroups take 224 each (128 x 56 + 256 x 224 = 384 x 168)
+  prefill2_work<T, REGS>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem,
+                         pairs - 1 - blockIdx.x, blockIdx.y, blockIdx.z, false);
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
@@ -120,10 +122,18 @@ void launch_t(const vattn_fwd_params_t& p, cudaStream_t stream) {
   const long long pair_items = (long long)((L.pp.num_m_tiles + 1) / 2) * p.num_heads * p.batch;
   if (p.seqlen_q > kBM && pair_items >= 148 && !env_int("VATTN_PREFILL_SINGLE", 0)) {
     const size_t smem = sizeof(Prefill2KernelSmem) + 1024;
-    VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((L.pp.num_m_tiles + 1) / 2, p.num_heads, p.batch);
-    prefill2_tc_kernel<T><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
-                                                                    L.vmap_tail, L.pp);
+    // VATTN_PREFILL_REGS=1: S row read from TMEM once and kept in registers (setmaxnreg); written but not
+    // yet measured, hence opt-in
+    if (env_int("VATTN_PREFILL_REGS", 0)) {
+      VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prefill2_tc_kernel<T, true><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
+                                                                            L.vmap_tail, L.pp);
+    } else {
+      VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prefill2_tc_kernel<T, false><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
+                                                                             L.vmap_tail, L.pp);
+    }
   } else {
     const size_t smem = sizeof(PrefillKernelSmem) + 1024;
     VATTN_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

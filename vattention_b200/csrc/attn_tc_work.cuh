@@ -533,6 +533,64 @@ __device__ __forceinline__ float tile_exp_store(uint32_t s_addr, uint32_t p_addr
   return (l0 + l1) + (l2 + l3);
 }
 
+// ---- register-resident S row (prefill2_work<T, true>) ------------------------------------------
+// With one softmax warp per scheduler nothing hides the TMEM read latency, and the two-pass scheme
+// above reads every S column twice (max pass, exp pass) with a wait after each 32-column load.
+// This variant reads the 128-column row ONCE -- four loads in flight, one wait -- and keeps it in
+// registers for both passes; it needs ~224 registers per softmax thread, which the kernel gets by
+// moving registers from the producer / MMA warpgroup with setmaxnreg.
+template <bool MASK>
+__device__ __forceinline__ float regs_quarter_max(const uint32_t (&r)[32], int key_base, int limit) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    float v0 = __uint_as_float(r[e]), v1 = __uint_as_float(r[e + 1]);
+    float v2 = __uint_as_float(r[e + 2]), v3 = __uint_as_float(r[e + 3]);
+    if (MASK) {
+      const int k = key_base + e;
+      if (k > limit) v0 = -INFINITY;
+      if (k + 1 > limit) v1 = -INFINITY;
+      if (k + 2 > limit) v2 = -INFINITY;
+      if (k + 3 > limit) v3 = -INFINITY;
+    }
+    m0 = fmaxf(m0, v0), m1 = fmaxf(m1, v1), m2 = fmaxf(m2, v2), m3 = fmaxf(m3, v3);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// exponentials of one 32-column quarter, packed to 16 bit into out[0..15]; adds to the four partial sums
+template <typename T, bool MASK>
+__device__ __forceinline__ void regs_quarter_exp(const uint32_t (&r)[32], uint32_t* out, float scale_log2,
+                                                 float mref, int key_base, int limit, float (&l)[4]) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    float p0 = fast_exp2(fmaf(__uint_as_float(r[e]), scale_log2, -mref));
+    float p1 = fast_exp2(fmaf(__uint_as_float(r[e + 1]), scale_log2, -mref));
+    float p2 = fast_exp2(fmaf(__uint_as_float(r[e + 2]), scale_log2, -mref));
+    float p3 = fast_exp2(fmaf(__uint_as_float(r[e + 3]), scale_log2, -mref));
+    if (MASK) {
+      const int k = key_base + e;
+      if (k > limit) p0 = 0.f;
+      if (k + 1 > limit) p1 = 0.f;
+      if (k + 2 > limit) p2 = 0.f;
+      if (k + 3 > limit) p3 = 0.f;
+    }
+    l[0] += p0, l[1] += p1, l[2] += p2, l[3] += p3;
+    out[e / 2] = Elem<T>::from_f2(p0, p1);
+    out[e / 2 + 1] = Elem<T>::from_f2(p2, p3);
+  }
+}
+
+// setmaxnreg (sm_90+): every warp of a warpgroup executes the same instruction
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 template <typename T>
 __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
                              const CUtensorMap* kmap_tail, const CUtensorMap* vmap_tail,
@@ -765,7 +823,7 @@ struct __align__(1024) Prefill2Smem {
   uint8_t ring[kPrefill2Stages][kTileBytes];
 };
 
-template <typename T>
+template <typename T, bool REGS = false>
 __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
                               const CUtensorMap* kmap_tail, const CUtensorMap* vmap_tail,
                               const PrefillParams& p, Prefill2Smem& sm, TcBarriers& bar, uint32_t tmem,
@@ -805,6 +863,9 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
   }
   __syncthreads();
 
+  // role split by warpgroup first, so that (REGS) each setmaxnreg dominates its role's code
+  if (warp < 4) {
+  if constexpr (REGS) setmaxnreg_dec<56>();
   if (warp == 0) {
     // =========================================================== TMA producer ====
     if (lane == 0 && n > 0) {
@@ -874,8 +935,10 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ==================================================== softmax / epilogue ====
+    if constexpr (REGS) setmaxnreg_inc<224>();
     const int t = (warp - 4) >> 2;            // which row block this warpgroup owns
     const int i = (threadIdx.x - 128) & 127;  // query row inside the block == TMEM lane
     const int sw = warp & 3;
@@ -894,7 +957,23 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       const int key0 = j * kBN;
       const bool need_mask = key0 + kBN - 1 > limit;
       const bool warp_mask = __any_sync(0xffffffffu, need_mask);
-      float mx = warp_mask ? tile_row_max<true>(s_addr, key0, limit) : tile_row_max<false>(s_addr, key0, limit);
+      uint32_t s0[REGS ? 32 : 1], s1[REGS ? 32 : 1], s2[REGS ? 32 : 1], s3[REGS ? 32 : 1];
+      float mx;
+      if constexpr (REGS) {
+        tmem_ld_x32(s_addr, s0);
+        tmem_ld_x32(s_addr + 32, s1);
+        tmem_ld_x32(s_addr + 64, s2);
+        tmem_ld_x32(s_addr + 96, s3);
+        tmem_wait_ld();
+        if (warp_mask)
+          mx = fmaxf(fmaxf(regs_quarter_max<true>(s0, key0, limit), regs_quarter_max<true>(s1, key0 + 32, limit)),
+                     fmaxf(regs_quarter_max<true>(s2, key0 + 64, limit), regs_quarter_max<true>(s3, key0 + 96, limit)));
+        else
+          mx = fmaxf(fmaxf(regs_quarter_max<false>(s0, 0, 0), regs_quarter_max<false>(s1, 0, 0)),
+                     fmaxf(regs_quarter_max<false>(s2, 0, 0), regs_quarter_max<false>(s3, 0, 0)));
+      } else {
+        mx = warp_mask ? tile_row_max<true>(s_addr, key0, limit) : tile_row_max<false>(s_addr, key0, limit);
+      }
       mx *= p.scale_log2;
       float alpha = 1.f;
       bool grow = mx > m_ref + kRescaleThreshold;
@@ -921,8 +1000,30 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       l *= alpha;
       const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
       // P_t(j) overwrites the already consumed low half of S_t (in place)
-      l += warp_mask ? tile_exp_store<T, true>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit)
-                     : tile_exp_store<T, false>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit);
+      if constexpr (REGS) {
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t packed[32];
+        if (warp_mask) {
+          regs_quarter_exp<T, true>(s0, packed, p.scale_log2, mref_safe, key0, limit, ls);
+          regs_quarter_exp<T, true>(s1, packed + 16, p.scale_log2, mref_safe, key0 + 32, limit, ls);
+        } else {
+          regs_quarter_exp<T, false>(s0, packed, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false>(s1, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
+        }
+        tmem_st_x32(s_addr, packed);  // keys 0..63 of P_t(j), 2 per column
+        if (warp_mask) {
+          regs_quarter_exp<T, true>(s2, packed, p.scale_log2, mref_safe, key0 + 64, limit, ls);
+          regs_quarter_exp<T, true>(s3, packed + 16, p.scale_log2, mref_safe, key0 + 96, limit, ls);
+        } else {
+          regs_quarter_exp<T, false>(s2, packed, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false>(s3, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
+        }
+        tmem_st_x32(s_addr + 32, packed);  // keys 64..127
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      } else {
+        l += warp_mask ? tile_exp_store<T, true>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit)
+                       : tile_exp_store<T, false>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit);
+      }
       tmem_wait_st();
       if ((j + 1) * kBN > lk) {
         const int pv = 2 * j + 1;
