@@ -19,7 +19,9 @@ VATTN_PREFILL_REGS=1 timeout 300 python -m pytest tests/test_gpu_attention.py -q
 for c in 512 2048 8192; do
   timeout 300 python scripts/bench_extra.py prefill --chunk $c
   VATTN_PREFILL_REGS=1 timeout 300 python scripts/bench_extra.py prefill --chunk $c
+  VATTN_PREFILL_REGS=2 timeout 300 python scripts/bench_extra.py prefill --chunk $c
 done
+VATTN_PREFILL_REGS=2 timeout 300 python -m pytest tests/test_gpu_attention.py -q --timeout 60 -k "prefill or pod or masked or lse" 2>&1 | tail -4
 echo "=== host-buffer entry points: parity (incl. the opt-in pipelined variant), then e2e with it"
 VATTN_TEST_PIPELINED=1 timeout 200 python -m pytest tests/test_zz_gpu_host_path.py -q --timeout 60 2>&1 | tail -5
 VATTN_E2E_PIPELINED=1 timeout 400 python bench.py --no-cpu | tee gpurun_out/bench_e2e_pipelined.json

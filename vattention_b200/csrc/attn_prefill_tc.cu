@@ -76,7 +76,7 @@ struct __align__(1024) Prefill2KernelSmem {
 };
 
 // two 128-row blocks per CTA with one softmax warpgroup each (prefill2_work)
-template <typename T, bool REGS>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kPrefill2Threads, 1)
 prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                    const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap kmap_tail,
@@ -101,7 +101,7 @@ prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   const int pairs = (p.num_m_tiles + 1) / 2;
   // REGS: 384 threads x 168 registers at launch; inside prefill2_work the producer / MMA warpgroup
   // drops to 56 and the two softmax warpgroups take 224 each (128 x 56 + 256 x 224 = 384 x 168)
-  prefill2_work<T, REGS>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem,
+  prefill2_work<T, MODE>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem,
                          pairs - 1 - blockIdx.x, blockIdx.y, blockIdx.z, false);
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
@@ -123,17 +123,16 @@ void launch_t(const vattn_fwd_params_t& p, cudaStream_t stream) {
   if (p.seqlen_q > kBM && pair_items >= 148 && !env_int("VATTN_PREFILL_SINGLE", 0)) {
     const size_t smem = sizeof(Prefill2KernelSmem) + 1024;
     dim3 grid((L.pp.num_m_tiles + 1) / 2, p.num_heads, p.batch);
-    // VATTN_PREFILL_REGS=1: S row read from TMEM once and kept in registers (setmaxnreg); written but not
-    // yet measured, hence opt-in
-    if (env_int("VATTN_PREFILL_REGS", 0)) {
-      VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prefill2_tc_kernel<T, true><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
-                                                                            L.vmap_tail, L.pp);
-    } else {
-      VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prefill2_tc_kernel<T, false><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
-                                                                             L.vmap_tail, L.pp);
-    }
+    // VATTN_PREFILL_REGS=1: S row read from TMEM once and kept in registers (setmaxnreg); =2: additionally
+    // one exponential in four on the FMA pipe (poly_exp2).  Written but not yet measured, hence opt-in
+    auto launch2 = [&](auto kernel) {
+      VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail, L.vmap_tail, L.pp);
+    };
+    const int mode = env_int("VATTN_PREFILL_REGS", 0);
+    if (mode == 2) launch2(prefill2_tc_kernel<T, 2>);
+    else if (mode == 1) launch2(prefill2_tc_kernel<T, 1>);
+    else launch2(prefill2_tc_kernel<T, 0>);
   } else {
     const size_t smem = sizeof(PrefillKernelSmem) + 1024;
     VATTN_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
