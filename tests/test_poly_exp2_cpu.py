@@ -11,7 +11,7 @@ SRC = Path(__file__).resolve().parent.parent / "vattention_b200" / "csrc" / "att
 
 def constants():
     body = SRC.read_text().split("__device__ __forceinline__ float poly_exp2(float x) {")[1].split("}")[0]
-    vals = [np.float32(v) for v in re.findall(r"([0-9]+\.[0-9]+)f", body)]
+    vals = [np.float32(v) for v in re.findall(r"([0-9]+\.[0-9]*)f", body)]
     # -126 clamp, magic (twice), c3, c2, c1, c0
     assert vals[0] == np.float32(126.0) and vals[1] == vals[2] == np.float32(12582912.0)
     return vals[3:7]
