@@ -28,7 +28,8 @@ VATTN_E2E_PIPELINED=1 timeout 400 python bench.py --no-cpu | tee gpurun_out/benc
 echo "=== headline decode: tiles per chunk beyond the cap of 16 (model: 32..64 may save a few % of waves)"
 for t in 0 16 32 64 128; do echo "tpc=$t"; VATTN_DECODE_TPC=$t $B decode --ctx 32768; done
 echo "=== fused o_proj kernel, world 1, dense ring"; timeout 120 python scripts/debug/oproj_latency.py
-echo "=== POD arms after the strategy switch"
-$B pod --prefills 1 --prefill-len 16384 --prefill-chunk 2048 --decodes 64 --decode-len 16384 --iters 10
-$B pod
+echo "=== POD arms after the strategy switch (+ the co-resident 'lean' strategy: parity first)"
+VATTN_TEST_POD_LEAN=1 timeout 200 python -m pytest tests/test_gpu_attention.py -q --timeout 60 -k "pod_fused_many" 2>&1 | tail -4
+$B pod --prefills 1 --prefill-len 16384 --prefill-chunk 2048 --decodes 64 --decode-len 16384 --iters 10 --lean
+$B pod --lean
 echo "=== done"

@@ -39,20 +39,24 @@ using namespace tcwork;
 constexpr int kStages = 3;               // 3 x 32 KB ring per CTA, 2 CTAs per SM
 constexpr int kMaxTilesPerChunk = 16;
 
-struct __align__(1024) DecodeKernelSmem {
-  DecodeSmemT<kStages> data;
+constexpr int kLeanStages = 2;            // co-resident POD arrangement: 2 x 32 KB ring beside a prefill CTA
+
+template <int STAGES>
+struct __align__(1024) DecodeKernelSmemT {
+  DecodeSmemT<STAGES> data;
   TcBarriers bar;
   uint32_t tmem_base;
 };
+using DecodeKernelSmem = DecodeKernelSmemT<kStages>;
 
-template <typename T, int GP>
+template <typename T, int GP, int STAGES = kStages>
 __global__ void __launch_bounds__(kThreads, 2)
 decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
                  const __grid_constant__ CUtensorMap kmap_tail, const __grid_constant__ CUtensorMap vmap_tail,
                  const DecodeTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  DecodeKernelSmem& sm =
-      *reinterpret_cast<DecodeKernelSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  DecodeKernelSmemT<STAGES>& sm =
+      *reinterpret_cast<DecodeKernelSmemT<STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
   if (warp == 0 && (threadIdx.x & 31) == 0) {
     prefetch_tensormap(&kmap);
@@ -66,8 +70,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  decode_work<T, GP, kStages>(&kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, blockIdx.x,
-                              blockIdx.y, blockIdx.z, false);
+  decode_work<T, GP, STAGES>(&kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, blockIdx.x,
+                             blockIdx.y, blockIdx.z, false);
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, kDecodeTmemCols);
 }
@@ -109,7 +113,8 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
   const int group = p.num_heads / p.num_kv_heads;
   DecodeTcLaunch L;
   build_decode_tc(p, ws, stream, &L);
-  const size_t smem = sizeof(DecodeKernelSmem) + 1024;
+  const bool lean = t_pod_lean;
+  const size_t smem = (lean ? sizeof(DecodeKernelSmemT<kLeanStages>) : sizeof(DecodeKernelSmem)) + 1024;
   dim3 grid(L.dp.num_chunks, p.num_kv_heads, p.batch);
   auto launch = [&](auto kernel) {
     // all GP instantiations share one function-pointer type, so a static flag here would be
@@ -119,7 +124,11 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
     kernel<<<grid, kThreads, smem, stream>>>(L.kmap, L.vmap, L.kmap_tail, L.vmap_tail, L.dp);
     timing_end(tslot, stream);
   };
-  if (group <= 4) launch(decode_tc_kernel<T, 4>);
+  if (lean) {
+    if (group <= 4) launch(decode_tc_kernel<T, 4, kLeanStages>);
+    else if (group <= 8) launch(decode_tc_kernel<T, 8, kLeanStages>);
+    else launch(decode_tc_kernel<T, 16, kLeanStages>);
+  } else if (group <= 4) launch(decode_tc_kernel<T, 4>);
   else if (group <= 8) launch(decode_tc_kernel<T, 8>);
   else launch(decode_tc_kernel<T, 16>);
   count_launch();

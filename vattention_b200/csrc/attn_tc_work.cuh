@@ -463,10 +463,12 @@ struct PrefillParams {
   int tail_rows;
 };
 
-struct __align__(1024) PrefillSmem {
+template <int STAGES>
+struct __align__(1024) PrefillSmemT {
   uint8_t q[kTile * kHeadDim * 2];
-  uint8_t ring[kPrefillStages][kTileBytes];
+  uint8_t ring[STAGES][kTileBytes];
 };
+using PrefillSmem = PrefillSmemT<kPrefillStages>;
 
 // Row max of one S tile (thread = query row).  MASK is a warp-uniform choice: interior tiles
 // (the vast majority) pay no per-element compare.  Four independent max chains: with one softmax
@@ -609,12 +611,16 @@ __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-template <typename T>
+// LEAN (the co-resident POD arrangement): P_j is written in place over the consumed half of S_j (the
+// next writer of that S buffer, QK^T of tile j+2, is issued after PV_j and the tensor core runs in
+// order), O lives in a second TMEM allocation `tmem_o`, and the ring is STAGES deep -- 384 TMEM
+// columns and 128 KB of shared memory instead of 512 / 192 KB, so that a decode CTA fits beside it.
+template <typename T, int STAGES = kPrefillStages, bool LEAN = false>
 __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
                              const CUtensorMap* kmap_tail, const CUtensorMap* vmap_tail,
-                             const PrefillParams& p, PrefillSmem& sm, TcBarriers& bar, uint32_t tmem, int mt,
-                             int h, int b, bool barriers_live) {
-  constexpr int kStages = kPrefillStages;
+                             const PrefillParams& p, PrefillSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem,
+                             int mt, int h, int b, bool barriers_live, uint32_t tmem_o = 0) {
+  constexpr int kStages = STAGES;
   constexpr int kBM = kTile, kBN = kTile, kD = kHeadDim;
   const int hkv = h / p.group;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -694,7 +700,8 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
 #pragma unroll
         for (int ks = 0; ks < kBN / 16; ks++) {
           // A: 16 keys = 8 packed TMEM columns of P_j; B: 16 key rows further down the V tile
-          umma_ts(tmem + kColO, tmem + kColP + (j & 1) * (kBN / 2) + ks * 8,
+          umma_ts(LEAN ? tmem_o : tmem + kColO,
+                  LEAN ? tmem + kColS + (j & 1) * kBN + ks * 8 : tmem + kColP + (j & 1) * (kBN / 2) + ks * 8,
                   make_smem_desc(v0 + ks * (16 * 128), p.v_lbo, p.v_sbo, kLayoutSw128), p.idesc_pv,
                   (j > 0 || ks > 0) ? 1u : 0u);
         }
@@ -748,18 +755,18 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
 #pragma unroll
         for (int c = 0; c < kD; c += 32) {
           uint32_t r[32];
-          tmem_ld_x32(tmem + lane_base + kColO + c, r);
+          tmem_ld_x32((LEAN ? tmem_o + lane_base + c : tmem + lane_base + kColO + c), r);
           tmem_wait_ld();
 #pragma unroll
           for (int e = 0; e < 32; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-          tmem_st_x32(tmem + lane_base + kColO + c, r);
+          tmem_st_x32((LEAN ? tmem_o + lane_base + c : tmem + lane_base + kColO + c), r);
         }
         tmem_wait_st();
       }
       l *= alpha;
       // pass 2: exponentials, row sum, pack to 16 bit, store P_j to TMEM
       const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
-      const uint32_t p_addr = tmem + lane_base + kColP + (j & 1) * (kBN / 2);
+      const uint32_t p_addr = LEAN ? s_addr : tmem + lane_base + kColP + (j & 1) * (kBN / 2);
       l += warp_mask ? tile_exp_store<T, true>(s_addr, p_addr, p.scale_log2, mref_safe, key0, limit)
                      : tile_exp_store<T, false>(s_addr, p_addr, p.scale_log2, mref_safe, key0, limit);
       tmem_wait_st();
@@ -797,7 +804,7 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
     for (int c = 0; c < kD; c += 32) {
       uint32_t r[32];
       if (n > 0) {
-        tmem_ld_x32(tmem + lane_base + kColO + c, r);
+        tmem_ld_x32((LEAN ? tmem_o + lane_base + c : tmem + lane_base + kColO + c), r);
         tmem_wait_ld();
       } else {
 #pragma unroll

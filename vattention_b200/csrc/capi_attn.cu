@@ -53,6 +53,8 @@ struct TimingState {
 } g_timing;
 }  // namespace
 
+thread_local bool t_pod_lean = false;  // attn_tc_host.h
+
 int timing_begin(cudaStream_t stream) {
   std::lock_guard<std::mutex> g(g_timing.mu);
   if (!g_timing.enabled) return -1;
@@ -310,20 +312,30 @@ PodSide& pod_side_for(cudaStream_t main) {
   }
   return s;
 }
-enum class PodStrategy { Streams, Kernel, Serial };
+struct LeanScope {  // marks the launches of one vattn_pod_fwd call as "lean" (attn_tc_host.h)
+  explicit LeanScope(bool on) { t_pod_lean = on; }
+  ~LeanScope() { t_pod_lean = false; }
+};
+enum class PodStrategy { Streams, Kernel, Serial, Lean };
 PodStrategy pod_strategy(int32_t fused_params) {
   // the reference: 15 = "pick the most suitable" (fused_api.cpp:24-53), anything else names one
   // tile configuration of its fused kernel.  Here: 15 -> the fastest measured arrangement, which is
   // the two specialised kernels co-scheduled on two streams (SM-level overlap by the block
   // scheduler; bench_extra.py pod: 1.13x over serial on a balanced hybrid batch where the
   // persistent single kernel is 0.89x); an explicit configuration -> the persistent fused kernel.
-  // VATTN_POD_STRATEGY=streams|kernel|serial overrides.
+  // VATTN_POD_STRATEGY=streams|kernel|serial|lean overrides.  "lean" = streams with the kernels'
+  // co-resident configurations (prefill: 128 KB, 384 TMEM columns; decode: 2-stage ring), prefill
+  // launched first so that every SM holds one prefill CTA and one decode CTA at the same time: the
+  // arrangement that should turn the overlap from SM-level partitioning into true sharing of an SM's
+  // tensor pipe and HBM queue.  Written, not yet measured: opt-in.
   if (const char* e = std::getenv("VATTN_POD_STRATEGY")) {
     const std::string v(e);
     if (v == "kernel") return PodStrategy::Kernel;
     if (v == "serial") return PodStrategy::Serial;
     if (v == "streams") return PodStrategy::Streams;
+    if (v == "lean") return PodStrategy::Lean;
   }
+  if (fused_params == 64) return PodStrategy::Lean;  // our own value: none of the reference's configurations
   return fused_params == 15 ? PodStrategy::Streams : PodStrategy::Kernel;
 }
 }  // namespace
@@ -348,6 +360,23 @@ int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* d
     const bool both = prefill && decode && prefill->batch > 0 && decode->batch > 0;
     const bool fork = both && strat != PodStrategy::Serial;
     PodSide* side = fork ? &pod_side_for(main) : nullptr;
+    std::string why;
+    if (fork && strat == PodStrategy::Lean && prefill->seqlen_q > 1 && decode->seqlen_q == 1 &&
+        prefill->impl != VATTN_IMPL_SIMT && decode->impl != VATTN_IMPL_SIMT &&
+        prefill_tc_supported(*prefill, &why) && decode_tc_supported(*decode, &why)) {
+      LeanScope lean(true);
+      vattn_fwd_params_t p = *prefill, d = *decode;
+      p.workspace = workspace, p.workspace_bytes = a;
+      d.workspace = workspace ? static_cast<char*>(workspace) + a : nullptr;
+      d.workspace_bytes = workspace_bytes > a ? workspace_bytes - a : 0;
+      VATTN_CUDA(cudaEventRecord(side->fork, main));
+      VATTN_CUDA(cudaStreamWaitEvent(side->side, side->fork, 0));
+      run_fwd(p, main);        // prefill first: one CTA per SM, leaving room for one decode CTA beside it
+      run_fwd(d, side->side);
+      VATTN_CUDA(cudaEventRecord(side->join, side->side));
+      VATTN_CUDA(cudaStreamWaitEvent(main, side->join, 0));
+      return VATTN_OK;
+    }
     if (decode) {
       vattn_fwd_params_t d = *decode;
       d.workspace = workspace ? static_cast<char*>(workspace) + a : nullptr;
