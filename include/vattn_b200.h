@@ -150,6 +150,9 @@ size_t vattn_get_pagemap(vattn_allocator_t* a, uint64_t* words, size_t cap_entri
  * (op: 1 reserve, 2 create, 3 map, 4 set_access, 5 unmap, 6 release, 7 addr_free) */
 size_t vattn_get_driver_log(vattn_allocator_t* a, uint64_t* words, size_t cap_records);
 void vattn_clear_driver_log(vattn_allocator_t* a);
+/* HOST_MOCK only: the mock driver's "device" holds `bytes` of physical memory: a create that
+ * would exceed it fails like cuMemCreate does when the device is full (0 = unlimited).       */
+void vattn_mock_set_capacity(vattn_allocator_t* a, uint64_t bytes);
 
 /* ------------------------------------------------------------------------ */
 /* Part B: attention over the contiguous K/V                                 */

@@ -363,3 +363,74 @@ def test_logical_pages_cleanup_balances_the_driver(mock_backend):
     assert n(3) > 0 and n(3) == n(5)          # map == unmap
     assert n(1) == n(7) == 4                   # reserve == addr_free (2 layers x K, V)
     va.init_kvcache(1, 1, 64, 1, 16384, 0, torch.float16, 2 * MB, False)   # leave a live config for the fixture
+
+
+def test_logical_reserve_stays_inside_the_budget(mock_backend):
+    """with sub-granularity pages reserve_physical_pages must not create more physical
+    memory than it was given; the per-(request, tensor) slack chunk is created only when a partly
+    used chunk actually appears, and never more than max_batch_size x tensors of them."""
+    page = 256 * 1024
+    L, B = 4, 8
+    budget = 64 * 2 * MB
+    va.init_kvcache(L, 2, 64, B, 32768, 0, torch.bfloat16, page, False)
+    va.clear_driver_log()
+    n = va.reserve_physical_pages(budget)
+    created = sum(r[2] for r in va.get_driver_log() if r[0] == 2)
+    assert n == budget // page - (budget // page) % (2 * L)
+    assert created <= budget and created >= n * page
+    # one token in every request: each (request, tensor) takes a whole chunk for one logical page
+    va.clear_driver_log()
+    va.step([1] * B, True)
+    extra = sum(r[2] for r in va.get_driver_log() if r[0] == 2)
+    assert extra == 0                      # 64 chunks budgeted, 8 requests x 8 tensors = 64 needed
+    tpp = va.get_config()["tokens_per_page"]
+    # fill until the budgeted chunks are gone: further partly used chunks come from the slack
+    lens = [1] * B
+    with pytest.raises(RuntimeError):
+        for _ in range(200):
+            lens = [x + tpp for x in lens]
+            va.step(lens, True)
+    total = sum(r[2] for r in va.get_driver_log() if r[0] == 2)
+    assert total <= B * 2 * L * 2 * MB     # never more than one slack chunk per (request, tensor)
+    st = va.get_state()
+    # after the OOM the books still balance: every logical page is either free or in the page map
+    in_map = sum(2 for _ in st["pagemap"])
+    assert in_map + len(st["pool"]) == n
+
+
+def test_reserve_failure_publishes_nothing_and_can_be_retried(mock_backend):
+    page = 256 * 1024
+    va.init_kvcache(2, 2, 64, 4, 32768, 0, torch.bfloat16, page, False)
+    va.mock_set_capacity(10 * 2 * MB)
+    with pytest.raises(RuntimeError, match="cuMemCreate failed"):
+        va.reserve_physical_pages(32 * 2 * MB)
+    assert va.get_state()["pool"] == []               # no logical page without a chunk behind it
+    assert va.num_free_kvblocks() == 0
+    va.mock_set_capacity(0)
+    assert va.reserve_physical_pages(32 * 2 * MB) == 32 * 8
+    va.step([5, 0, 0, 0], True)
+    assert va.get_state()["mapped_pages"] == [1, 0, 0, 0]
+
+
+def test_grow_rolls_back_when_the_driver_fails_mid_block(mock_backend):
+    """2 MiB pages: cuMemCreate is not on the grow path, so fail the slack chunk creation of the
+    logical mode instead -- block k of a request fails in layer 1 after layer 0 was mapped."""
+    page = 256 * 1024
+    L, B = 2, 2
+    va.init_kvcache(L, 2, 64, B, 32768, 0, torch.bfloat16, page, False)
+    n = va.reserve_physical_pages(4 * 2 * MB)        # 4 chunks = exactly one per (request 0, tensor)
+    va.step([1, 0], True)                            # request 0 holds all 4 chunks, one page each
+    before = va.get_state()
+    # request 1 now needs slack chunks; let the device hold only one more -> K of layer 0 maps,
+    # V of layer 0 fails
+    va.mock_set_capacity(5 * 2 * MB)
+    with pytest.raises(RuntimeError, match="cuMemCreate failed"):
+        va.step([1, 1], True)
+    after = va.get_state()
+    assert after["mapped_pages"] == before["mapped_pages"]
+    assert after["pool"] == before["pool"]           # LIFO order restored
+    assert after["pagemap"] == before["pagemap"]
+    va.mock_set_capacity(0)
+    va.step([1, 1], True)                            # and the same step succeeds afterwards
+    assert va.get_state()["mapped_pages"] == [1, 1]
+    assert len(va.get_state()["pool"]) == n - 2 * 2 * L

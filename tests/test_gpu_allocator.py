@@ -246,3 +246,48 @@ def test_megacache_tensor_core_path_respects_unmapped_pages():
     wantp = ref.attn_with_kvcache_ref(qp, kref[0:1], vref[0:1], cache_seqlens=total, causal=True)
     scale = wantp.float().abs().max().item()
     assert (outp.float().cpu() - wantp.float()).abs().max().item() <= 3e-3 * scale + 2 ** -7 * scale
+
+
+def test_map_common_pages_alias_on_the_real_driver():
+    """Prefix sharing (vattention.cu:325-373, mux.h:68-85): after map_common_pages the SAME physical
+    page backs the first blocks of every request -- bytes written through request 0's view are read
+    back through request 1's and 2's; attention over either view gives the same result; physical
+    memory is charged once; unmapping returns every page exactly once (oracle: ref-counted pool)."""
+    L, Hkv, D, B, ctx = 2, 8, 128, 3, 8192
+    ts = va.init_kvcache(L, Hkv, D, B, ctx, 0, torch.bfloat16, 2 * MB, False)
+    n_pages = va.reserve_physical_pages(48 * MB)
+    tpp = va.get_config()["tokens_per_page"]
+    va.map_common_pages(tpp + 1)                     # 2 blocks shared by all 3 requests
+    st = va.get_state()
+    assert st["mapped_pages"] == [2, 2, 2]
+    assert len(st["pool"]) == n_pages - 2 * 2 * L    # 2 blocks x (K, V) x L layers -- not x 3 requests
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 2 * tpp
+    for t in ts:
+        t[0, :n].normal_(generator=g)                # write through request 0's virtual range only
+    torch.cuda.synchronize()
+    for t in ts:
+        assert torch.equal(t[1, :n], t[0, :n]) and torch.equal(t[2, :n], t[0, :n])
+    # a write through request 2 is seen by request 0 as well (aliases, not copies)
+    ts[0][2, 5].fill_(3.0)
+    torch.cuda.synchronize()
+    assert torch.equal(ts[0][0, 5], torch.full_like(ts[0][0, 5], 3.0))
+    # decode attention over the shared prefix: three requests, one physical copy
+    q = torch.randn(1, 1, 32, D, device="cuda", generator=g).bfloat16().expand(B, 1, 32, D).contiguous()
+    lens = torch.full((B,), n, dtype=torch.int32, device="cuda")
+    out = att.flash_attn_with_kvcache(q, ts[0][:, :n], ts[L][:, :n], cache_seqlens=lens, causal=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])
+    want = ref.attn_with_kvcache_ref(q[:1].cpu(), ts[0][:1, :n].cpu(), ts[L][:1, :n].cpu(),
+                                     cache_seqlens=lens[:1].cpu(), causal=True)
+    err = (out[:1].float().cpu() - want.float()).abs().max().item()
+    assert err <= 3e-3 * want.float().abs().max().item() + 1e-3
+    # private growth on top of the shared prefix stays private
+    va.step([n + 5, n, n], True)
+    ts[0][0, n:n + 5].fill_(7.0)
+    torch.cuda.synchronize()
+    assert va.get_state()["mapped_pages"] == [3, 2, 2]
+    va.step([0, 0, 0], True)                         # eager reclaim unmaps everything
+    st = va.get_state()
+    assert st["mapped_pages"] == [0, 0, 0]
+    assert sorted(st["pool"]) == list(range(n_pages))   # every page back exactly once

@@ -1,0 +1,190 @@
+"""GPU parity at the FULL sizes of BASELINE.json's configs, against the reference's own dispatch
+target on identical inputs: flash_attn.flash_attn_with_kvcache (the library the sarathi
+vattention wrappers call, vattention_flashattention_wrapper.py:159-166,194-205) -- and, on sampled
+rows, against the fp32 oracle (oracle/attention_ref.py).
+
+    configs[1]  Llama-3-8B, B64, 32K context, decode with a fused one-token append, shuffled
+                cache_batch_idx, bf16 and fp16; caches bit-identical to the library's afterwards
+    configs[2]  Yi-6B-200K, 128K context, chunked prefill: chunk 2048 at p = 0 and p = 126 976,
+                chunk 512 at p = 130 560 (K/V in a vAttention tensor with 256 KB logical pages)
+    configs[3]  POD: 8 x 16K prefill + 56 x 4K decode, Llama-3-8B, fp16, fused_params 9 and 15
+    configs[4]  Llama-3-70B TP-8 per-GPU shape (Hq 8, Hkv 1), B16, 32K / 128K decode
+
+Tolerance (north_star: "within 1e-3 rel (bf16/fp16)"), written out:
+    |ours - lib|  <=  1e-3 * max|lib|  +  one output ulp of |lib_i|
+Both sides round their result to 16 bit, so two exact computations may land on neighbouring
+representable values: the ulp term is that and nothing else (bf16: 2^-7 |x|, fp16: 2^-10 |x|).
+The measured maxima are appended to gpurun_out/parity_full_configs.jsonl for the record.
+Same pattern as the reference's assertions, pod_attn/tests/attn_sweep.py:82-97.
+"""
+import json
+import os
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import attention_ref as ref
+from vattention_b200 import attention as att
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = Path(__file__).resolve().parent.parent
+ULP = {torch.bfloat16: 2.0 ** -7, torch.float16: 2.0 ** -10}
+
+
+def fa_or_skip():
+    fa = pytest.importorskip("flash_attn")
+    return fa.flash_attn_with_kvcache
+
+
+def record(name, **kw):
+    try:
+        out = ROOT / "gpurun_out"
+        out.mkdir(exist_ok=True)
+        with open(out / "parity_full_configs.jsonl", "a") as f:
+            f.write(json.dumps({"case": name, **kw}) + "\n")
+    except OSError:
+        pass
+
+
+def assert_close_to_library(name, ours, lib, dtype, rel=1e-3):
+    """|ours - lib| <= rel * max|lib| + one output ulp of |lib_i| (chunked to bound memory)."""
+    assert ours.shape == lib.shape and ours.dtype == lib.dtype == dtype
+    scale = lib.float().abs().max().item()
+    worst, worst_excess, bad = 0.0, 0.0, 0
+    o2, l2 = ours.reshape(-1, ours.shape[-1]), lib.reshape(-1, lib.shape[-1])
+    step = 1 << 18
+    for i in range(0, o2.shape[0], step):
+        a, b = o2[i:i + step].float(), l2[i:i + step].float()
+        err = (a - b).abs()
+        tol = rel * scale + ULP[dtype] * b.abs()
+        worst = max(worst, err.max().item())
+        worst_excess = max(worst_excess, (err - tol).max().item())
+        bad += int((err > tol).sum().item())
+    record(name, dtype=str(dtype), max_abs_diff=worst, scale=scale, max_diff_over_scale=worst / scale,
+           elements=int(ours.numel()), outside_tolerance=bad)
+    assert bad == 0, (f"{name}: {bad} of {ours.numel()} elements outside 1e-3*scale + 1 ulp; "
+                      f"max |ours-lib| {worst:.3e} = {worst / scale:.2e} of scale {scale:.3f}")
+    assert not torch.isnan(ours).any()
+
+
+def close_to_oracle(out, want, dtype):
+    """fp32 oracle: 1e-3 (fp16) / 3e-3 (bf16: P rounded to 8 bits, see test_gpu_attention.close)
+    of max|ref| plus one output ulp."""
+    out, want = out.float().cpu(), want.float().cpu()
+    atol = {torch.bfloat16: 3e-3, torch.float16: 1e-3}[dtype]
+    tol = atol * want.abs().max().item() + ULP[dtype] * want.abs() + 1e-6
+    err = (out - want).abs()
+    assert not (err > tol).any(), f"max err {err.max().item():.3e} vs tol {tol.max().item():.3e}"
+
+
+# ------------------------------------------------------------------ configs[1] / configs[4] ----
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("name,B,Hq,Hkv,ctx,ragged", [
+    ("configs1_llama3_8b_B64_32k", 64, 32, 8, 32768, False),
+    ("configs1_llama3_8b_B64_32k_ragged", 64, 32, 8, 32768, True),
+    ("configs4_llama3_70b_tp8_B16_32k", 16, 8, 1, 32768, False),
+    ("configs4_llama3_70b_tp8_B16_128k", 16, 8, 1, 131072, True),
+])
+def test_decode_full_config_matches_library(name, B, Hq, Hkv, ctx, ragged, dtype):
+    fa = fa_or_skip()
+    D = 128
+    g = torch.Generator(device=DEV).manual_seed(11)
+    slots = B + 3                                 # more cache slots than requests, shuffled mapping
+    kc = torch.empty(slots, ctx, Hkv, D, device=DEV, dtype=dtype).normal_(generator=g)   # 4.5 GB at configs[1]
+    vc = torch.empty(slots, ctx, Hkv, D, device=DEV, dtype=dtype).normal_(generator=g)
+    q = torch.randn(B, 1, Hq, D, device=DEV, generator=g).to(dtype)
+    kn = torch.randn(B, 1, Hkv, D, device=DEV, generator=g).to(dtype)
+    vn = torch.randn(B, 1, Hkv, D, device=DEV, generator=g).to(dtype)
+    if ragged:
+        lens = torch.randint(ctx // 2, ctx, (B,), device=DEV, generator=g).int()
+        lens[0], lens[1] = ctx - 1, 0             # longest possible; an empty sequence that only sees its new token
+    else:
+        lens = torch.full((B,), ctx - 1, device=DEV, dtype=torch.int32)
+    idx = torch.randperm(slots, device=DEV, generator=g)[:B].int()
+    kc2, vc2 = kc.clone(), vc.clone()
+    want = fa(q, kc2, vc2, kn, vn, cache_seqlens=lens, cache_batch_idx=idx, causal=True)
+    out = att.flash_attn_with_kvcache(q, kc, vc, kn, vn, cache_seqlens=lens, cache_batch_idx=idx, causal=True)
+    torch.cuda.synchronize()
+    assert_close_to_library(name, out, want, dtype)
+    assert torch.equal(kc, kc2) and torch.equal(vc, vc2), "caches differ after the append"
+    # three rows against the fp32 oracle (the appended token is already in the cache: no k/v here)
+    sub = [0, B // 2, B - 1]
+    sl = idx[sub].long()
+    got = ref.attn_with_kvcache_ref(q[sub].cpu(), kc[sl].cpu(), vc[sl].cpu(),
+                                    cache_seqlens=(lens[sub] + 1).cpu())
+    close_to_oracle(out[sub], got, dtype)
+    del kc, vc, kc2, vc2
+    torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------ configs[2] ----
+@pytest.mark.parametrize("chunk,p", [(2048, 0), (2048, 126976), (512, 130560)])
+def test_chunked_prefill_yi6b_128k_matches_library(chunk, p):
+    """One chunk of the 128K chunked prefill, K/V in a vAttention tensor with the fi_vattn_256kb
+    page bookkeeping (256 KB logical pages over 2 MiB chunks)."""
+    fa = fa_or_skip()
+    from vattention_b200 import vattention as va
+    Hq, Hkv, D, S = 32, 4, 128, 131072
+    dtype = torch.bfloat16
+    torch.zeros(1, device=DEV)
+    kc, vc = va.init_kvcache(1, Hkv, D, 1, S, 0, dtype, 256 << 10, False)
+    try:
+        va.reserve_physical_pages(2 * S * Hkv * D * 2 + (8 << 20))
+        va.step([p + chunk], True)
+        g = torch.Generator(device=DEV).manual_seed(5 + p)
+        kc[0, :p + chunk].normal_(generator=g)
+        vc[0, :p + chunk].normal_(generator=g)
+        q = torch.randn(1, chunk, Hq, D, device=DEV, generator=g).to(dtype)
+        total = torch.tensor([p + chunk], dtype=torch.int32, device=DEV)
+        kv, vv = kc[:, :p + chunk], vc[:, :p + chunk]         # the wrapper's slice (wrapper.py:157-166)
+        want = fa(q, kv, vv, cache_seqlens=total, causal=True)
+        out = att.flash_attn_with_kvcache(q, kv, vv, cache_seqlens=total, causal=True)
+        torch.cuda.synchronize()
+        assert_close_to_library(f"configs2_yi6b_chunk{chunk}_p{p}", out, want, dtype)
+        # first and last 32 rows of the chunk against the fp32 oracle, 4 q heads (one per kv head)
+        hs = [0, 9, 18, 27]
+        kcpu, vcpu = kc[:1, :p + chunk].cpu(), vc[:1, :p + chunk].cpu()
+        for r0 in (0, chunk - 32):
+            n_k = p + r0 + 32
+            want32 = ref.attn_with_kvcache_ref(q[:, r0:r0 + 32][:, :, hs].cpu(), kcpu[:, :n_k], vcpu[:, :n_k],
+                                               cache_seqlens=torch.tensor([n_k], dtype=torch.int32), causal=True)
+            close_to_oracle(out[:, r0:r0 + 32][:, :, hs], want32, dtype)
+    finally:
+        va.cleanup()
+
+
+# ------------------------------------------------------------------------------ configs[3] ----
+@pytest.mark.parametrize("fused_params", [15, 9])
+def test_pod_8x16k_prefill_56x4k_decode_matches_library(fused_params):
+    fa = fa_or_skip()
+    Hq, Hkv, D = 32, 8, 128
+    Bp, Sp, Bd, Sd = 8, 16384, 56, 4096
+    dtype = torch.float16
+    g = torch.Generator(device=DEV).manual_seed(3)
+    q_p = torch.randn(Bp, Sp, Hq, D, device=DEV, generator=g).to(dtype)
+    kc_p = torch.randn(Bp, Sp, Hkv, D, device=DEV, generator=g).to(dtype)
+    vc_p = torch.randn(Bp, Sp, Hkv, D, device=DEV, generator=g).to(dtype)
+    lens_p = torch.full((Bp,), Sp, dtype=torch.int32, device=DEV)
+    q_d = torch.randn(Bd, 1, Hq, D, device=DEV, generator=g).to(dtype)
+    kc_d = torch.randn(Bd, Sd, Hkv, D, device=DEV, generator=g).to(dtype)
+    vc_d = torch.randn(Bd, Sd, Hkv, D, device=DEV, generator=g).to(dtype)
+    kn = torch.randn(Bd, 1, Hkv, D, device=DEV, generator=g).to(dtype)
+    vn = torch.randn(Bd, 1, Hkv, D, device=DEV, generator=g).to(dtype)
+    lens_d = torch.randint(Sd // 2, Sd, (Bd,), device=DEV, generator=g).int()
+    lens_d[0] = Sd - 1
+    idx = torch.randperm(Bd, device=DEV, generator=g).int()
+    kc_d2, vc_d2 = kc_d.clone(), vc_d.clone()
+    want_p = fa(q_p, kc_p, vc_p, cache_seqlens=lens_p, causal=True)
+    want_d = fa(q_d, kc_d2, vc_d2, kn, vn, cache_seqlens=lens_d, cache_batch_idx=idx, causal=True)
+    out_p, out_d = att.true_fused_attn_with_kvcache(q_p, kc_p, vc_p, q_d, kc_d, vc_d, kn, vn, causal=True,
+                                                    cache_seqlens_p=lens_p, cache_seqlens_d=lens_d,
+                                                    cache_batch_idx=idx, fused_params=fused_params)
+    torch.cuda.synchronize()
+    assert_close_to_library(f"configs3_pod_prefill_fp{fused_params}", out_p, want_p, dtype)
+    assert_close_to_library(f"configs3_pod_decode_fp{fused_params}", out_d, want_d, dtype)
+    assert torch.equal(kc_d, kc_d2) and torch.equal(vc_d, vc_d2)
+    # the fused call equals the two separate calls of this library bit for bit (POD's contract)
+    sep_p = att.flash_attn_with_kvcache(q_p, kc_p, vc_p, cache_seqlens=lens_p, causal=True)
+    assert torch.equal(sep_p, out_p)

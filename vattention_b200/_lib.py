@@ -103,6 +103,7 @@ _SIGS = {
     "vattn_get_pagemap": (C.c_size_t, [_A, _P(C.c_uint64), C.c_size_t]),
     "vattn_get_driver_log": (C.c_size_t, [_A, _P(C.c_uint64), C.c_size_t]),
     "vattn_clear_driver_log": (None, [_A]),
+    "vattn_mock_set_capacity": (None, [_A, C.c_uint64]),
     "vattn_fwd_kvcache_workspace": (C.c_size_t, [_P(FwdParams)]),
     "vattn_fwd_kvcache": (C.c_int, [_P(FwdParams), C.c_void_p]),
     "vattn_single_prefill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64,

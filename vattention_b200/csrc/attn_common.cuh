@@ -38,6 +38,19 @@ inline void cuda_check(cudaError_t e, const char* what) {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// SM count of the current device (cudaDevAttrMultiProcessorCount; 148 on a B200), cached per device
+inline int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // Partial results of a split-KV pass: per (batch, q_row, q_head, split) an
 // un-normalised fp32 accumulator of head_dim values plus (running max in the
 // log2 domain, running sum).  Layout:

@@ -88,12 +88,12 @@ int tiles_per_chunk_for(const vattn_fwd_params_t& p) {
   }
   const int64_t nt = (p.seqlen_k + kTile - 1) / kTile;
   const int64_t total = nt * p.batch * p.num_kv_heads;
-  // one chunk per resident CTA slot (148 SMs x 2) when the problem is small, chunks of at most 16
+  // one chunk per resident CTA slot (SMs x 2) when the problem is small, chunks of at most 16
   // tiles (2048 keys) when it is large.  Measured (profiles/r1_decode_chunk_sweep.jsonl): the
   // per-CTA prologue (TMEM, barriers, Q, ring fill) and the split combine cost more than an uneven
   // last wave -- B16 x Hkv1 x 32K runs 72.7 us with 16-tile chunks, 91 us with 4, 180 us with 1
   static const int forced = env_int("VATTN_DECODE_TPC", 0);
-  const int64_t slots = 148 * 2;
+  const int64_t slots = (int64_t)num_sms() * 2;
   int64_t tpc = total / slots;
   if (tpc < 1) tpc = 1;
   if (tpc > kMaxTilesPerChunk) tpc = kMaxTilesPerChunk;

@@ -138,9 +138,7 @@ void launch_pod_t(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, 
   sch.n_decode = (long long)Dl.dp.num_chunks * dec.num_kv_heads * dec.batch;
   VATTN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
   if (!decode_tc_fuses_append(dec)) launch_append_kv(dec, stream);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = num_sms();
   const long long total = sch.n_prefill + sch.n_decode;
   const int grid = (int)(total < sms ? total : sms);
   const size_t smem = sizeof(PodSmem) + 1024;

@@ -170,7 +170,7 @@ void launch_t(const vattn_fwd_params_t& p, cudaStream_t stream) {
     dim3 grid(L.pp.num_m_tiles, p.num_heads, p.batch);
     prefill_lean_tc_kernel<T><<<grid, kThreads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail, L.vmap_tail,
                                                                 L.pp);
-  } else if (p.seqlen_q > kBM && pair_items >= 148 && !env_int("VATTN_PREFILL_SINGLE", 0)) {
+  } else if (p.seqlen_q > kBM && pair_items >= num_sms() && !env_int("VATTN_PREFILL_SINGLE", 0)) {
     const size_t smem = sizeof(Prefill2KernelSmem) + 1024;
     dim3 grid((L.pp.num_m_tiles + 1) / 2, p.num_heads, p.batch);
     // VATTN_PREFILL_REGS=1: S row read from TMEM once and kept in registers (setmaxnreg); =2: additionally

@@ -53,10 +53,12 @@ attn_simt_kernel(const SimtParams p) {
   constexpr int RPL = 32 / LPR;     // rows per warp-wide load
   constexpr int RPI = RPL * kUnroll;  // rows per warp per iteration
 
-  const int split = blockIdx.x;
+  // query rows on grid.x (up to 2^31 - 1 blocks: a 128K-token prefill has more rows than the 65535
+  // that grid.y / grid.z allow), splits on grid.z (<= 128)
+  const int split = blockIdx.z;
   const int hkv = blockIdx.y / p.chunks_per_group;
   const int hchunk = blockIdx.y % p.chunks_per_group;
-  const int row_id = blockIdx.z;  // b * seqlen_q + i
+  const int row_id = blockIdx.x;  // b * seqlen_q + i
   const int b = row_id / p.seqlen_q;
   const int qi = row_id - b * p.seqlen_q;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -343,7 +345,7 @@ void launch_simt_t(const vattn_fwd_params_t& p, int splits, const SplitWorkspace
   sp.scale_log2 = p.softmax_scale * kLog2e;
   const int gq = sp.group >= 8 ? 8 : (sp.group > 2 ? 4 : sp.group);
   sp.chunks_per_group = (sp.group + gq - 1) / gq;
-  dim3 grid(splits, p.num_kv_heads * sp.chunks_per_group, p.batch * p.seqlen_q);
+  dim3 grid(p.batch * p.seqlen_q, p.num_kv_heads * sp.chunks_per_group, splits);
   dim3 block(kWarps * 32);
   const int tslot = timing_begin(stream);
   switch (gq) {
@@ -383,7 +385,7 @@ int simt_num_splits(const vattn_fwd_params_t& p) {
   const int group = p.num_heads / p.num_kv_heads;
   const int gq = group >= 8 ? 8 : (group > 2 ? 4 : group);
   const int64_t base = (int64_t)p.batch * p.seqlen_q * p.num_kv_heads * ((group + gq - 1) / gq);
-  const int64_t target = 148 * 4 * 4;
+  const int64_t target = (int64_t)num_sms() * 4 * 4;
   int64_t s = (target + base - 1) / base;
   const int max_by_len = (p.seqlen_k + (p.k_new ? p.seqlen_new : 0) + 255) / 256;
   if (s > max_by_len) s = max_by_len;

@@ -80,7 +80,7 @@ append_kv_kernel(const char* __restrict__ k_new, const char* __restrict__ v_new,
 
 inline int grid_for(int64_t total_threads) {
   int64_t blocks = (total_threads + kThreads - 1) / kThreads;
-  const int64_t cap = 148 * 8;  // 8 resident CTAs of 256 threads per SM
+  const int64_t cap = (int64_t)num_sms() * 8;  // 8 resident CTAs of 256 threads per SM
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;

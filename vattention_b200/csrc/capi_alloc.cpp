@@ -87,9 +87,13 @@ int vattn_create(vattn_allocator_t** out, int backend) {
 
 int vattn_destroy(vattn_allocator_t* a) {
   if (!a) return VATTN_OK;
+  // the handle is freed even when cleanup() rethrows a stored mapper-thread error
+  struct Reaper {
+    vattn_allocator_t* h;
+    ~Reaper() { delete h; }
+  } reaper{a};
   VATTN_TRY
   if (a->impl) a->impl->cleanup();
-  delete a;
   return VATTN_OK;
   VATTN_CATCH
 }
@@ -320,6 +324,13 @@ size_t vattn_get_driver_log(vattn_allocator_t* a, uint64_t* words, size_t cap_re
     words[4 * i + 3] = log[i].handle;
   }
   return log.size();
+}
+
+void vattn_mock_set_capacity(vattn_allocator_t* a, uint64_t bytes) {
+  if (check_handle(a) && a->mock) {
+    a->impl->wait_background();
+    a->mock->set_capacity(bytes);
+  }
 }
 
 void vattn_clear_driver_log(vattn_allocator_t* a) {

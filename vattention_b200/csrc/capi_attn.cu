@@ -110,6 +110,15 @@ void validate(const vattn_fwd_params_t& p) {
     // flash_api.cpp:1454 -- the sarathi wrapper pattern-matches this text
     if (p.seqlen_new > p.seqlen_k)
       throw ArgError("If key is supplied, it must have seqlen <= the seqlen of the KV cache");
+    // without cache_seqlens the append row would be seqlen_k itself: one row past the cache view
+    // (possibly unmapped virtual memory)
+    if (!p.cache_seqlens)
+      throw ArgError("[vattn] cache_seqlens is required when k / v are appended");
+    // the append / rotary kernels read k and v with 16-byte vector loads
+    const int64_t ns[] = {p.knew_batch_stride, p.knew_row_stride, p.knew_head_stride,
+                          p.vnew_batch_stride, p.vnew_row_stride, p.vnew_head_stride};
+    for (int64_t s : ns)
+      if (s % 8 != 0) throw ArgError("[vattn] strides must be multiples of 8 elements");
   }
   if ((p.rotary_cos == nullptr) != (p.rotary_sin == nullptr))
     throw ArgError("If rotary cos is provided, rotary sin must also be provided");  // flash_api.cpp:1516
@@ -186,13 +195,13 @@ void run_fwd(const vattn_fwd_params_t& p_in, cudaStream_t stream) {
   }
 }
 
-// device staging arena for the host-buffer entry point
+// device staging arena for the host-buffer entry point; one per caller stream: the lock only
+// serialises the enqueue, so calls on two streams must not share staged q / k / out
 struct HostStage {
   void* dev = nullptr;
   size_t cap = 0;
   void* ws = nullptr;
   size_t ws_cap = 0;
-  std::mutex mu;
   void ensure(void** ptr, size_t* cap_, size_t bytes) {
     if (*cap_ >= bytes) return;
     if (*ptr) cudaFree(*ptr);
@@ -202,7 +211,8 @@ struct HostStage {
     *cap_ = bytes;
   }
 };
-HostStage g_stage;
+std::mutex g_stage_mu;
+std::unordered_map<cudaStream_t, HostStage> g_stages;
 
 }  // namespace
 }  // namespace vattn
@@ -431,7 +441,8 @@ static int fwd_kvcache_host_impl(const vattn_fwd_params_t* hp, void* stream_, bo
     if (hp->rotary_cos || hp->rotary_sin)
       throw UnsupportedError("[vattn] the host-buffer entry point takes no rotary tables (device-resident "
                              "cos/sin go through vattn_fwd_kvcache)");
-    std::lock_guard<std::mutex> g(g_stage.mu);
+    std::lock_guard<std::mutex> g(g_stage_mu);
+    HostStage& g_stage = g_stages[stream];
     const size_t eb = 2;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t q_bytes = (size_t)hp->batch * hp->seqlen_q * hp->num_heads * hp->head_dim * eb;

@@ -151,21 +151,40 @@ u64 KvAllocator::reserve_physical_pages(u64 free_memory) {
   u64 n = free_memory / cfg_.page_size;
   n -= n % (2 * cfg_.num_layers);
   log("Reserving " + std::to_string(n) + " pages of size " + std::to_string(cfg_.page_size) + " ...");
-  const u64 before = pool_.size();
-  while (pool_.size() < n) {
-    PhysPage p;
-    p.handle = logical() ? 0 : drv_->create(cfg_.page_size);
-    p.id = created_++;
-    pool_.push_back(p);
+  if (!logical()) {
+    while (pool_.size() < n) {
+      PhysPage p;
+      p.handle = drv_->create(cfg_.page_size);
+      p.id = created_++;
+      pool_.push_back(p);
+    }
+    return pool_.size();
   }
-  if (logical() && pool_.size() > before) {
-    // chunks for the new logical bytes, plus one per (request, tensor) for internal fragmentation
-    // (a request's last chunk in a tensor may hold fewer than phys_group pages)
-    const u64 tensors = 2 * (cfg_.megacache ? 1 : cfg_.num_layers);
-    u64 want = (pool_.size() * cfg_.page_size + cfg_.granularity - 1) / cfg_.granularity +
-               cfg_.max_batch_size * tensors;
-    u64 have = chunk_pool_.size() + chunks_.size();
-    for (; have < want; have++) chunk_pool_.push_back(drv_->create(cfg_.granularity));
+  // Logical (sub-granularity) pages: physical memory moves in 2 MiB chunks.  The chunks that back
+  // the new logical bytes are created FIRST -- if the driver runs out, nothing has been published
+  // and the call can be retried -- and total exactly free_memory (rounded up to one chunk).  The
+  // extra chunk a request needs when the last chunk of one of its tensors is only partly used is
+  // created on demand (chunk_ref), at most max_batch_size x tensors of them over the allocator's
+  // life: the budget is exceeded only by fragmentation that actually occurs, never up front.
+  if (pool_.size() < n) {
+    const u64 want = (n * cfg_.page_size + cfg_.granularity - 1) / cfg_.granularity;
+    const size_t had = chunk_pool_.size();
+    try {
+      for (u64 have = chunk_pool_.size() + chunks_.size() - slack_chunks_; have < want; have++)
+        chunk_pool_.push_back(drv_->create(cfg_.granularity));
+    } catch (...) {
+      while (chunk_pool_.size() > had) {
+        drv_->release(chunk_pool_.back());
+        chunk_pool_.pop_back();
+      }
+      throw;
+    }
+    while (pool_.size() < n) {
+      PhysPage p;
+      p.handle = 0;
+      p.id = created_++;
+      pool_.push_back(p);
+    }
   }
   return pool_.size();
 }
@@ -194,12 +213,23 @@ PhysPage KvAllocator::pop_page() {
 
 void KvAllocator::map_pair(u64 req, u64 layer, u64 off, PhysPage k, PhysPage v) {
   // cudaInternal.h:70-82 minus the per-page cuMemSetAccess (batched by callers)
+  // either both halves are mapped and recorded, or neither
   if (logical()) {
     chunk_ref(k_ptr_[layer], off);
-    chunk_ref(v_ptr_[layer], off);
+    try {
+      chunk_ref(v_ptr_[layer], off);
+    } catch (...) {
+      chunk_unref(k_ptr_[layer], off);
+      throw;
+    }
   } else {
     drv_->map(k_ptr_[layer] + off, cfg_.page_size, k.handle);
-    drv_->map(v_ptr_[layer] + off, cfg_.page_size, v.handle);
+    try {
+      drv_->map(v_ptr_[layer] + off, cfg_.page_size, v.handle);
+    } catch (...) {
+      drv_->unmap(k_ptr_[layer] + off, cfg_.page_size);
+      throw;
+    }
   }
   pagemap_[Key(req, off, layer)] = std::make_pair(k, v);
 }
@@ -211,11 +241,22 @@ void KvAllocator::chunk_ref(u64 base, u64 off) {
     it->second.second++;
     return;
   }
-  if (chunk_pool_.empty()) throw OomError("***** page pool is empty *****");
+  if (chunk_pool_.empty()) {
+    // every budgeted chunk is in use and this (request, tensor) starts a new, partly used one
+    const u64 tensors = 2 * (cfg_.megacache ? 1 : cfg_.num_layers);
+    if (slack_chunks_ >= cfg_.max_batch_size * tensors) throw OomError("***** page pool is empty *****");
+    chunk_pool_.push_back(drv_->create(cfg_.granularity));  // may throw: nothing has been changed yet
+    slack_chunks_++;
+  }
   const u64 h = chunk_pool_.back();
-  chunk_pool_.pop_back();
   drv_->map(va, cfg_.granularity, h);
-  drv_->set_access(va, cfg_.granularity);
+  try {
+    drv_->set_access(va, cfg_.granularity);
+  } catch (...) {
+    drv_->unmap(va, cfg_.granularity);
+    throw;
+  }
+  chunk_pool_.pop_back();
   chunks_[va] = std::make_pair(h, (u64)1);
 }
 
@@ -247,10 +288,49 @@ void KvAllocator::grow(u64 req, u64 nblocks, bool sync, u64* pages_counter) {
   for (u64 count = 0; count < nblocks; count++) {
     u64 off = base + mapped_pages_[req] * cfg_.page_size;  // utils.h:185-191
     if (!(off < (req + 1) * cfg_.per_req)) break;          // vattention.cu:254-266
-    for (u64 layer = 0; layer < nl; layer++) {
-      PhysPage k = pop_page();  // K first, then V (mux.h:40-42)
-      PhysPage v = pop_page();
-      map_pair(req, layer, off, k, v);
+    u64 layer = 0;
+    try {
+      for (; layer < nl; layer++) {
+        PhysPage k = pop_page();  // K first, then V (mux.h:40-42)
+        PhysPage v;
+        try {
+          v = pop_page();
+        } catch (...) {
+          pool_.push_back(k);
+          throw;
+        }
+        try {
+          map_pair(req, layer, off, k, v);
+        } catch (...) {
+          pool_.push_back(v);  // restore the LIFO order: K was popped first
+          pool_.push_back(k);
+          throw;
+        }
+      }
+    } catch (...) {
+      // undo the layers of this block that were already mapped (reverse order), then let the
+      // blocks completed before it stand: page map, pool and mapped_pages_ stay consistent
+      while (layer-- > 0) {
+        auto it = pagemap_.find(Key(req, off, layer));
+        if (logical()) {
+          chunk_unref(k_ptr_[layer], off);
+          chunk_unref(v_ptr_[layer], off);
+        } else {
+          drv_->unmap(k_ptr_[layer] + off, cfg_.page_size);
+          drv_->unmap(v_ptr_[layer] + off, cfg_.page_size);
+        }
+        pool_.push_back(it->second.second);
+        pool_.push_back(it->second.first);
+        pagemap_.erase(it);
+      }
+      if (done) {
+        for (u64 l2 = 0; l2 < nl && !logical(); l2++) {
+          drv_->set_access(k_ptr_[l2] + first_off, done * cfg_.page_size);
+          drv_->set_access(v_ptr_[l2] + first_off, done * cfg_.page_size);
+        }
+        if (pages_counter) *pages_counter += done * 2 * nl;
+      }
+      throw;
     }
     mapped_pages_[req]++;
     done++;
@@ -534,6 +614,7 @@ void KvAllocator::cleanup() {
   for (u64 h : chunk_pool_) drv_->release(h);
   chunk_pool_.clear();
   chunks_.clear();
+  slack_chunks_ = 0;
   pool_.clear();
   pagemap_.clear();
   shared_refs_.clear();

@@ -137,6 +137,7 @@ class KvAllocator {
   std::unordered_map<u64, u64> shared_refs_;  // page id -> live mappings (map_common_pages)
   // logical mode: physical chunk pool and, per chunk VA, (handle, number of logical pages inside)
   std::vector<u64> chunk_pool_;
+  u64 slack_chunks_ = 0;  // chunks created on demand for partly used last chunks (<= B x tensors)
   std::unordered_map<u64, std::pair<u64, u64>> chunks_;
   std::vector<u64> mapped_pages_, seq_lens_;
 

@@ -287,7 +287,7 @@ int vattn_oproj_allreduce(const void* x, int64_t x_row_stride, const void* w, vo
     static const int forced_tile = std::getenv("VATTN_OPROJ_NTILE") ? std::atoi(std::getenv("VATTN_OPROJ_NTILE")) : 0;
     static const int k_rot = std::getenv("VATTN_OPROJ_KROT") ? std::atoi(std::getenv("VATTN_OPROJ_KROT")) : 5;
     for (int n : {32, 64, 128})
-      if (hidden % n == 0 && hidden / n <= 148 && n >= forced_tile) {
+      if (hidden % n == 0 && hidden / n <= num_sms() && n >= forced_tile) {
         n_tile = n;
         break;
       }

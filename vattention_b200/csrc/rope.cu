@@ -146,7 +146,7 @@ vattn_fwd_params_t launch_rope(const vattn_fwd_params_t& p, cudaStream_t stream)
   const int64_t vecs =
       (int64_t)p.batch * (p.seqlen_q * p.num_heads + p.seqlen_new * p.num_kv_heads) * (p.head_dim / 8);
   int64_t blocks = (vecs + kThreads - 1) / kThreads;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   auto go = [&](auto tag) {
     using T = decltype(tag);
     rope_qk_kernel<T><<<(int)blocks, kThreads, 0, stream>>>(

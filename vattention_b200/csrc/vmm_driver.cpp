@@ -36,7 +36,11 @@ u64 MockVmmDriver::create(u64 size) {
   u64 h;
   {
     std::lock_guard<std::mutex> g(mu_);
+    if (capacity_ && in_use_ + size > capacity_)
+      throw std::runtime_error("[vattn] cuMemCreate failed (mock device out of memory)");
     h = next_handle_++;
+    in_use_ += size;
+    sizes_[h] = size;
   }
   log(OP_CREATE, 0, size, h);
   return h;
@@ -45,7 +49,17 @@ u64 MockVmmDriver::create(u64 size) {
 void MockVmmDriver::map(u64 va, u64 size, u64 handle) { log(OP_MAP, va, size, handle); }
 void MockVmmDriver::set_access(u64 va, u64 size) { log(OP_SET_ACCESS, va, size, 0); }
 void MockVmmDriver::unmap(u64 va, u64 size) { log(OP_UNMAP, va, size, 0); }
-void MockVmmDriver::release(u64 handle) { log(OP_RELEASE, 0, 0, handle); }
+void MockVmmDriver::release(u64 handle) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = sizes_.find(handle);
+    if (it != sizes_.end()) {
+      in_use_ -= it->second;
+      sizes_.erase(it);
+    }
+  }
+  log(OP_RELEASE, 0, 0, handle);
+}
 void MockVmmDriver::addr_free(u64 va, u64 size) { log(OP_ADDR_FREE, va, size, 0); }
 
 std::vector<DriverLogRecord> MockVmmDriver::snapshot_log() {

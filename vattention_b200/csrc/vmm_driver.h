@@ -11,6 +11,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace vattn {
@@ -74,12 +75,15 @@ class MockVmmDriver : public VmmDriver {
 
   std::vector<DriverLogRecord> snapshot_log();
   void clear_log();
+  void set_capacity(u64 bytes) { capacity_ = bytes; }  // 0 = unlimited
 
  private:
   void log(u64 op, u64 va, u64 size, u64 h);
   u64 gran_;
   u64 next_va_ = 0x7f0000000000ull;  // fake VA space, never dereferenced
   u64 next_handle_ = 1;
+  u64 capacity_ = 0, in_use_ = 0;
+  std::unordered_map<u64, u64> sizes_;
   std::mutex mu_;
   std::vector<DriverLogRecord> log_;
 };

@@ -293,3 +293,8 @@ def get_driver_log() -> list:
 
 def clear_driver_log() -> None:
     lib.vattn_clear_driver_log(_get())
+
+
+def mock_set_capacity(nbytes: int) -> None:
+    """HOST_MOCK only: physical bytes the mock device can hold (0 = unlimited)."""
+    lib.vattn_mock_set_capacity(_get(), int(nbytes))
