@@ -151,11 +151,10 @@ def pod_ref(q_p, k_cache_p, v_cache_p, q_d, k_cache_d, v_cache_d, k=None, v=None
 def sdpa_decode_cpu(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float) -> torch.Tensor:
     """BASELINE.json configs[0]: '1-seq 8-head x 128-dim 1K-ctx decode attn via torch SDPA on CPU'.
     q [B,1,Hq,D], k/v [B,L,Hkv,D] already holding the appended token.  Used as the timed CPU
-    baseline (bench.py) -- torch's own fused CPU kernel, not the loop above."""
-    B, _, Hq, D = q.shape
-    Hkv = k.shape[2]
+    baseline (bench.py) -- torch's own fused CPU kernel, not the loop above; GQA through SDPA's
+    enable_gqa so that no 4x copy of K/V is materialised inside the timed region."""
     qq = q.transpose(1, 2)                                  # [B,Hq,1,D]
-    kk = k.transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
-    vv = v.transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
-    o = torch.nn.functional.scaled_dot_product_attention(qq, kk, vv, is_causal=False, scale=scale)
+    kk, vv = k.transpose(1, 2), v.transpose(1, 2)           # [B,Hkv,L,D] views: no copy of K/V
+    o = torch.nn.functional.scaled_dot_product_attention(qq, kk, vv, is_causal=False, scale=scale,
+                                                         enable_gqa=True)
     return o.transpose(1, 2)

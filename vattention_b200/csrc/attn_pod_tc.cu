@@ -129,7 +129,7 @@ void launch_pod_t(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, 
   PrefillTcLaunch P;
   DecodeTcLaunch Dl;
   build_prefill_tc(pre, &P);
-  build_decode_tc(dec, dec_ws, stream, &Dl);
+  build_decode_tc(dec, dec_ws, stream, &Dl, false);
   PodSched sch;
   sch.counter = counter;
   sch.prefill_blocks = pre.seqlen_q > kTile ? 2 : 1;
@@ -177,7 +177,7 @@ bool pod_tc_supported(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& d
 }
 
 size_t pod_tc_workspace(const vattn_fwd_params_t&, const vattn_fwd_params_t& dec) {
-  return 256 + decode_tc_workspace(dec);
+  return 256 + decode_tc_workspace_grid(dec);
 }
 
 void launch_pod_tc(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec, void* ws, size_t ws_bytes,

@@ -10,9 +10,13 @@ struct DecodeTcLaunch {
   tcwork::DecodeTcParams dp;
   CUtensorMap kmap, vmap, kmap_tail, vmap_tail;
   SplitWorkspace ws;
+  bool stream_k = false;  // device-side stream-K schedule (decode_sk_kernel) instead of the chunk grid
+  int sk_ctas = 0;
 };
 // fills kernel parameters + TMA maps for a seqlen_q == 1 problem; `ws` receives the split partials
-void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream, DecodeTcLaunch* out);
+// (allow_stream_k = false: the classic chunk grid's parameters, as the POD kernel's decode items use them)
+void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream, DecodeTcLaunch* out,
+                     bool allow_stream_k);
 // true when the decode kernel itself appends k_new/v_new (one new token per sequence)
 bool decode_tc_fuses_append(const vattn_fwd_params_t& p);
 
@@ -30,6 +34,7 @@ extern thread_local bool t_pod_lean;
 bool decode_tc_supported(const vattn_fwd_params_t& p, std::string* why);
 bool prefill_tc_supported(const vattn_fwd_params_t& p, std::string* why);
 size_t decode_tc_workspace(const vattn_fwd_params_t& p);
+size_t decode_tc_workspace_grid(const vattn_fwd_params_t& p);
 void launch_combine(const vattn_fwd_params_t& p, int splits, const SplitWorkspace& ws, cudaStream_t stream);
 
 }  // namespace vattn

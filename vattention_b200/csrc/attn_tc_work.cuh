@@ -113,29 +113,41 @@ struct __align__(1024) DecodeSmemT {
   int ticket;                        // arrival order of this chunk among its sequence's chunks
 };
 
+// One contiguous run of key tiles of one (batch entry, kv head): what a CTA processes between two
+// (re)initialisations of its pipeline.  The classic grid makes one segment per (chunk, kv head, batch)
+// CTA; the stream-K schedule cuts the flattened tile space into equal ranges per persistent CTA and a
+// range contributes one segment per sequence it touches.
+struct DecodeSegment {
+  int b, hkv;
+  int tile0, n;        // first key tile, number of key tiles (0: only the appended token, or nothing)
+  int len;             // cached rows of the sequence (without the token appended by this launch)
+  bool owns_new;       // this segment folds in / writes the appended token
+  int parts;           // segments the sequence is split into (1: the result is final)
+  // partial (acc, m, l) of head g of this segment goes to index part_idx + g * part_stride_g;
+  // the reducer reads part c of head g at red_idx + g * red_stride_g + c * red_stride_c
+  int64_t part_idx, part_stride_g, red_idx, red_stride_g, red_stride_c;
+  bool publish_empty;  // nothing to do, but the separate combine kernel expects a slot: write (-inf, 0)
+};
+
 template <typename T, int GP, int STAGES>
-__device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, const CUtensorMap* kmap_tail,
-                            const CUtensorMap* vmap_tail, const DecodeTcParams& p,
-                            DecodeSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem, int chunk, int hkv,
-                            int b, bool barriers_live) {
+__device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap, const CUtensorMap* kmap_tail,
+                               const CUtensorMap* vmap_tail, const DecodeTcParams& p,
+                               DecodeSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem, const DecodeSegment& seg,
+                               bool barriers_live) {
   static_assert(STAGES <= kMaxStages, "ring deeper than the barrier block");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = seg.b, hkv = seg.hkv;
   const int slot = p.cache_batch_idx ? p.cache_batch_idx[b] : b;
-  const bool fused_new = p.k_new != nullptr;
-  // rows read from the cache; with a fused append the new token is NOT read back from memory
-  const int len = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + (fused_new ? 0 : p.seqlen_new);
-  const int ntiles_seq = (len + kTile - 1) / kTile;
-  const int chunks_active = max(1, (ntiles_seq + p.tiles_per_chunk - 1) / p.tiles_per_chunk);
-  const int tile0 = chunk * p.tiles_per_chunk;
-  const int n = max(0, min(p.tiles_per_chunk, ntiles_seq - tile0));  // tiles of this item
-  const bool owns_new = fused_new && chunk == chunks_active - 1;
+  const int len = seg.len;
+  const int tile0 = seg.tile0;
+  const int n = seg.n;
+  const bool owns_new = seg.owns_new;
   const int G = p.group;
   const int h0 = hkv * G;
 
-  if (chunk >= chunks_active) {  // CTA-uniform: this chunk lies past the sequence
-    // with the separate combine kernel every slot must hold something: publish an empty partial
-    if (!p.arrive && threadIdx.x < G) {
-      const int64_t base = ((int64_t)b * p.num_heads + h0 + threadIdx.x) * p.num_chunks + chunk;
+  if (seg.publish_empty) {  // CTA-uniform: this chunk lies past the sequence
+    if (threadIdx.x < G) {
+      const int64_t base = seg.part_idx + threadIdx.x * seg.part_stride_g;
       p.ws_ml[base * 2] = -INFINITY;
       p.ws_ml[base * 2 + 1] = 0.f;
     }
@@ -382,15 +394,14 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
       }
     }
 
-    // one chunk covers the whole sequence: final result.  Otherwise publish the partial; it is
-    // reduced either by the last chunk of the sequence to arrive (p.arrive) or by combine_kernel.
-    bool write_out = p.arrive ? chunks_active == 1 : p.num_chunks == 1;
+    // one segment covers the whole sequence: final result.  Otherwise publish the partial; it is
+    // reduced either by the last segment of the sequence to arrive (p.arrive) or by combine_kernel.
+    bool write_out = seg.parts == 1;
     if (!write_out) {
-      // publish this chunk's partial; the last chunk of the sequence to arrive reduces them all
 #pragma unroll
       for (int g = 0; g < GP; g++) {
         if (g >= G) continue;
-        const int64_t base = ((int64_t)b * p.num_heads + h0 + g) * p.num_chunks + chunk;
+        const int64_t base = seg.part_idx + g * seg.part_stride_g;
         p.ws_acc[base * kHeadDim + t] = acc[g];
         if (t == 0) {
           p.ws_ml[base * 2] = m_run[g];
@@ -407,20 +418,21 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
         }
         named_bar_sync(1, 128);
       }
-      if (p.arrive && sm.ticket == chunks_active - 1) {
+      if (p.arrive && sm.ticket == seg.parts - 1) {
         __threadfence();
         write_out = true;
 #pragma unroll
         for (int g = 0; g < GP; g++) {
           if (g >= G) continue;
-          const int64_t base = ((int64_t)b * p.num_heads + h0 + g) * p.num_chunks;
+          const int64_t base = seg.red_idx + g * seg.red_stride_g;
           float M = -INFINITY;
-          for (int c = 0; c < chunks_active; c++) M = fmaxf(M, __ldcg(p.ws_ml + (base + c) * 2));
+          for (int c = 0; c < seg.parts; c++) M = fmaxf(M, __ldcg(p.ws_ml + (base + c * seg.red_stride_c) * 2));
           float o = 0.f, L = 0.f;
-          for (int c = 0; c < chunks_active; c++) {
-            const float w = fast_exp2(__ldcg(p.ws_ml + (base + c) * 2) - M);
-            L = fmaf(__ldcg(p.ws_ml + (base + c) * 2 + 1), w, L);
-            o = fmaf(__ldcg(p.ws_acc + (base + c) * kHeadDim + t), w, o);
+          for (int c = 0; c < seg.parts; c++) {
+            const int64_t idx = base + c * seg.red_stride_c;
+            const float w = fast_exp2(__ldcg(p.ws_ml + idx * 2) - M);
+            L = fmaf(__ldcg(p.ws_ml + idx * 2 + 1), w, L);
+            o = fmaf(__ldcg(p.ws_acc + idx * kHeadDim + t), w, o);
           }
           acc[g] = o, Lg[g] = L, m_run[g] = M;
         }
@@ -442,6 +454,62 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
   }
   tc_fence_before();
   __syncthreads();
+}
+
+// Classic grid: one segment per (chunk of tiles_per_chunk tiles, kv head, batch entry); partial layout
+// [batch][q head][chunk] as combine_kernel reads it.
+template <typename T, int GP, int STAGES>
+__device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, const CUtensorMap* kmap_tail,
+                            const CUtensorMap* vmap_tail, const DecodeTcParams& p,
+                            DecodeSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem, int chunk, int hkv,
+                            int b, bool barriers_live) {
+  const bool fused_new = p.k_new != nullptr;
+  DecodeSegment seg;
+  seg.b = b, seg.hkv = hkv;
+  // rows read from the cache; with a fused append the new token is NOT read back from memory
+  seg.len = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + (fused_new ? 0 : p.seqlen_new);
+  const int ntiles_seq = (seg.len + kTile - 1) / kTile;
+  const int chunks_active = max(1, (ntiles_seq + p.tiles_per_chunk - 1) / p.tiles_per_chunk);
+  seg.tile0 = chunk * p.tiles_per_chunk;
+  seg.n = max(0, min(p.tiles_per_chunk, ntiles_seq - seg.tile0));
+  seg.owns_new = fused_new && chunk == chunks_active - 1;
+  const int64_t row = ((int64_t)b * p.num_heads + hkv * p.group) * p.num_chunks;
+  seg.part_idx = row + chunk, seg.part_stride_g = p.num_chunks;
+  seg.red_idx = row, seg.red_stride_g = p.num_chunks, seg.red_stride_c = 1;
+  // with the in-kernel reduction only the active chunks count; the combine kernel reads every slot
+  seg.parts = p.arrive ? chunks_active : p.num_chunks;
+  seg.publish_empty = false;
+  if (chunk >= chunks_active) {
+    if (p.arrive) return;
+    seg.publish_empty = true;
+  }
+  // an empty sequence with nothing appended: with the separate combine kernel its slot 0 must be a
+  // well-formed empty partial too (the combine then writes the zeros / +inf lse)
+  if (seg.n == 0 && !seg.owns_new && !p.arrive && p.num_chunks > 1) seg.publish_empty = true;
+  decode_segment<T, GP, STAGES>(kmap, vmap, kmap_tail, vmap_tail, p, sm, bar, tmem, seg, barriers_live);
+}
+
+// ---- stream-K schedule over the flattened (batch, kv head, key tile) space ---------------------
+// Every sequence contributes max(1, ceil(len / 128)) virtual tiles per kv head (a sequence with no
+// cached rows still needs its output written), batch-major.  G persistent CTAs cut the T virtual
+// tiles into G equal ranges (the first T mod G one tile longer); a range contributes one segment per
+// sequence it touches.  Segment ids `cta + sequence ordinal` are unique and increase along the tile
+// axis, so the parts of one sequence occupy consecutive partial slots; the last part to arrive
+// reduces them (p.arrive).  All of it is computed on the device from cache_seqlens: the launch
+// shape depends neither on the lengths nor on the extent of the cache view.
+struct StreamKPlan {
+  int64_t total;   // T
+  int64_t q;       // T / G
+  int r;           // T % G
+  int ctas;        // G
+};
+__device__ __forceinline__ int64_t sk_range_begin(const StreamKPlan& pl, int c) {
+  return (int64_t)c * pl.q + (c < pl.r ? c : pl.r);
+}
+__device__ __forceinline__ int sk_cta_of(const StreamKPlan& pl, int64_t x) {
+  const int64_t big = (int64_t)pl.r * (pl.q + 1);
+  if (x < big) return (int)(x / (pl.q + 1));
+  return pl.r + (int)((x - big) / pl.q);  // q > 0 here: x >= big implies tiles remain for the short ranges
 }
 
 // ======================================================================= prefill ====

@@ -112,10 +112,11 @@ class _VAttentionWrapperBase:
     def _views(self, t: torch.Tensor, n_heads: int) -> torch.Tensor:
         return t.reshape(-1, n_heads, self.head_dim)
 
-    def _save_chunk(self, key, value, kv_cache, index: int, start: int, n: int, offset: int):
+    def _save_chunk(self, key, value, kv_cache, index: int, start: int, n: int, offset: int,
+                    end: Optional[int] = None):
         k = self._views(key[start:start + n], self.num_kv_heads)
         v = self._views(value[start:start + n], self.num_kv_heads)
-        self.ops.cache_flat(k, v, kv_cache[0][index][offset:], kv_cache[1][index][offset:], "auto")
+        self.ops.cache_flat(k, v, kv_cache[0][index][offset:end], kv_cache[1][index][offset:end], "auto")
 
     def _decode(self, query, key, value, kv_cache, token_offset: int, softmax_scale, full_cache: bool):
         n = self.decode_batch_size
@@ -177,7 +178,8 @@ class VAttentionFlashInferWrapper(_VAttentionWrapperBase):
         off = 0
         for idx, (done, n) in enumerate(zip(self.prefill_cache_lens, self.prefill_query_lens)):
             index = int(self.batch_index[idx])
-            self._save_chunk(key, value, kv_cache, index, off, n, done)
+            # the FI wrapper slices the cache to the chunk's end first (flashinfer_wrapper.py:140-148)
+            self._save_chunk(key, value, kv_cache, index, off, n, done, done + n)
             q = self._views(query[off:off + n], self.num_q_heads)
             o = self.ops.single_prefill_with_kv_cache(q, kv_cache[0][index][:done + n],
                                                       kv_cache[1][index][:done + n], causal=True)
