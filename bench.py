@@ -159,13 +159,17 @@ def algorithmic_bytes(total_len_after_append: float, hq, hkv, batch) -> int:
 ULP = {torch.bfloat16: 2.0 ** -7, torch.float16: 2.0 ** -10}
 
 
-def close_to_library(ours, lib, rel=1e-3):
-    """|ours - lib| <= rel * max|lib| + one output ulp of |lib_i|  ->  (ok, max_diff / scale)."""
+def close_to_library(ours, lib):
+    """bf16 criterion of tests/test_gpu_baseline_configs.py: rms(ours - lib) <= 1e-3 * max|lib| and
+    |ours - lib| <= 8e-3 * max|lib| + one output ulp of |lib_i| (two implementations that both round
+    P to bf16, as FA-2 does, differ by that much at 32K keys)  ->  (ok, max_diff / scale, rms / scale)."""
     a, b = ours.float(), lib.float()
-    scale = b.abs().max().item()
+    scale = max(b.abs().max().item(), 1e-30)
     err = (a - b).abs()
-    bad = int((err > rel * scale + ULP[ours.dtype] * b.abs()).sum().item())
-    return bad == 0 and not bool(torch.isnan(a).any()), err.max().item() / max(scale, 1e-30)
+    bad = int((err > 8e-3 * scale + ULP[ours.dtype] * b.abs()).sum().item())
+    rms = float((err.double() ** 2).mean().sqrt().item())
+    ok = bad == 0 and rms <= 1e-3 * scale and not bool(torch.isnan(a).any())
+    return ok, err.max().item() / scale, rms / scale
 
 
 def fp32_decode_rows(q, kc, vc, lens_after, slots, rows, scale):
@@ -539,10 +543,11 @@ def parity_check(att, dist, dev, rank, world, wl, shard, tp_attn, w_o, q0, kn0, 
                                       softmax_scale=scale, causal=True)
     torch.cuda.synchronize(dev)
     if want is not None:
-        ok, rel = close_to_library(out, want)
+        ok, rel, rms = close_to_library(out, want)
         rows_ours = torch.stack([kv[slot_of[b], seq_lens[b]] for b in (0, B // 2, B - 1)])
-        res["vs_flash_attn"] = {"ok": ok, "max_diff_over_scale": round(rel, 6),
-                                "tolerance": "1e-3 * max|lib| + 1 bf16 ulp of |lib_i|",
+        res["vs_flash_attn"] = {"ok": ok, "max_diff_over_scale": round(rel, 6), "rms_diff_over_scale": round(rms, 6),
+                                "tolerance": "rms <= 1e-3 * max|lib|, max <= 8e-3 * max|lib| + 1 bf16 ulp "
+                                             "(bf16 P rounding, see tests/test_gpu_baseline_configs.py)",
                                 "appended_rows_bit_identical": bool(torch.equal(rows_ours, rows_lib))}
         if not ok or not torch.equal(rows_ours, rows_lib):
             raise RuntimeError(f"parity_check failed against flash_attn: {res}")
@@ -553,6 +558,10 @@ def parity_check(att, dist, dev, rank, world, wl, shard, tp_attn, w_o, q0, kn0, 
     ok32 = bool((err <= 3e-3 * s + ULP[DTYPE] * ref.abs()).all())
     res["vs_fp32_rows"] = {"ok": ok32, "rows": rows, "max_err_over_scale": round(err.max().item() / s, 6),
                            "tolerance": "3e-3 * max|ref| + 1 bf16 ulp (P is rounded to bf16 as in FA-2)"}
+    if want is not None:
+        e_lib = (want[rows].float() - ref).abs().max().item()
+        res["vs_fp32_rows"]["library_max_err_over_scale"] = round(e_lib / s, 6)
+        ok32 = ok32 and err.max().item() <= 1.5 * e_lib + ULP[DTYPE] * s
     if not ok32:
         raise RuntimeError(f"parity_check failed against the fp32 reference: {res}")
     if world > 1:
