@@ -196,10 +196,10 @@ def load_reference_wrapper(kind):
     return getattr(m, cls)
 
 
-def mixed_batch(kind, dtype=torch.float32, device="cpu"):
+def mixed_batch(kind, dtype=torch.float32, device="cpu", D=64):
     """One prefill chunk and three decodes, flat [tokens, H*D] tensors (the model runner's layout)."""
     g = torch.Generator().manual_seed(0)
-    Hq, Hkv, D, B, ctx = 4, 2, 128 if device != "cpu" else 64, 5, 256
+    Hq, Hkv, B, ctx = 4, 2, 5, 256
     kc = torch.randn(B, ctx, Hkv, D, generator=g).to(dtype)
     vc = torch.randn(B, ctx, Hkv, D, generator=g).to(dtype)
     # the reference's POD wrapper hands cache_flat the un-offset cache (pod_wrapper.py:153-158): only
@@ -344,14 +344,14 @@ def test_shims_with_the_cuda_operators_match_the_oracle(kind):
                                     true_fused_attn_with_kvcache=fused.true_fused_attn_with_kvcache,
                                     cache_flat=cache_flat)
         assert fa_mod.__version__ == "vattention_b200" and hasattr(vattention, "step_async")
-    batch = mixed_batch(kind, dtype=torch.float16, device="cuda:0")
+    batch = mixed_batch(kind, dtype=torch.float16, device="cuda:0", D=128)
     dims = batch[0]
     w = get_attention_wrapper_class(kind)(ops=ops).init(num_q_heads=dims[0], num_kv_heads=dims[1], head_dim=dims[2],
                                                         device=torch.device("cuda:0"))
     out = run_iteration(w, kind, batch, device="cuda:0")
     torch.cuda.synchronize()
     _, caches, mds, qkv, slots, p, decs, done = batch
-    fresh = mixed_batch(kind, dtype=torch.float16, device="cpu")
+    fresh = mixed_batch(kind, dtype=torch.float16, device="cpu", D=128)
     want, kc, vc = expected(kind, dims, fresh[1], fresh[3], slots, p, decs, done, dims[2] ** -0.5)
     err = (out.float().cpu() - want.float()).abs().max().item()
     assert err <= 1e-3 * want.float().abs().max().item() + 2.0 ** -10 * want.float().abs().max().item()

@@ -358,12 +358,17 @@ def test_pod_fused_many_items_matches_oracle(dtype, fused_params):
         close(out_p, want_p, dtype)
         close(out_d, want_d, dtype)
     assert torch.equal(kd.cpu(), kc_r) and torch.equal(vd.cpu(), vc_r)
-    # fused == the two separate calls, bit for bit (same work functions)
+    # fused vs the two separate calls: the auto strategy (15) launches the very same kernels, bit for
+    # bit; the persistent fused kernel (explicit configuration) splits the keys at other points than
+    # the stand-alone stream-K schedules, so it agrees to rounding
     sep_p = att.flash_attn_with_kvcache(d(q_p), d(kc_p), d(vc_p), cache_seqlens=d(lens_p), causal=True)
     sep_d = att.flash_attn_with_kvcache(d(q_d), kd, vd, d(kn), d(vn), cache_seqlens=d(lens_d),
                                         cache_batch_idx=d(idx), causal=True)  # re-appends the same rows
-    assert torch.equal(out_p, sep_p)
-    assert torch.equal(out_d, sep_d)
+    if fused_params == 15:
+        assert torch.equal(out_p, sep_p) and torch.equal(out_d, sep_d)
+    else:
+        close(out_p, sep_p, dtype)
+        close(out_d, sep_d, dtype)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])

@@ -51,6 +51,13 @@ inline int num_sms() {
   return cached[dev];
 }
 
+// Zero-initialised arrival counters for the in-kernel reductions of the stream-K kernels ("the last
+// part of an item to arrive reduces its partials"; the kernels reset what they used).  One slice of
+// a per-device pool per (stream, user): two launches on different streams may overlap in time, and
+// the pool is created once, so no allocation happens on a stream that is being captured into a CUDA
+// graph (capi_attn.cu).
+int* arrival_counters(cudaStream_t stream, int user, size_t need);
+
 // Partial results of a split-KV pass: per (batch, q_row, q_head, split) an
 // un-normalised fp32 accumulator of head_dim values plus (running max in the
 // log2 domain, running sum).  Layout:

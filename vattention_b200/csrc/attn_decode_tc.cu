@@ -300,20 +300,7 @@ static int env_int_(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-int* decode_arrive_counters(cudaStream_t stream, size_t need) {
-  static std::mutex mu;
-  static std::unordered_map<cudaStream_t, std::pair<int*, size_t>> bufs;
-  std::lock_guard<std::mutex> g(mu);
-  auto& e = bufs[stream];
-  if (e.second < need) {
-    if (e.first) cudaFree(e.first);
-    const size_t n = need < 65536 ? 65536 : need;
-    VATTN_CUDA(cudaMalloc(&e.first, n * sizeof(int)));
-    VATTN_CUDA(cudaMemset(e.first, 0, n * sizeof(int)));
-    e.second = n;
-  }
-  return e.first;
-}
+int* decode_arrive_counters(cudaStream_t stream, size_t need) { return arrival_counters(stream, 0, need); }
 
 bool decode_tc_fuses_append(const vattn_fwd_params_t& p) { return p.k_new != nullptr && p.seqlen_new == 1; }
 

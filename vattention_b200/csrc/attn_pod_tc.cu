@@ -17,6 +17,8 @@
 // Work items are the same device functions the stand-alone kernels run (attn_tc_work.cuh), so
 // each output equals the separate call's bit for bit (the reference asserts allclose(1e-3),
 // pod_attn/tests/attn_sweep.py:82-97).
+#include <climits>
+
 #include "attn_common.cuh"
 #include "attn_tc_host.h"
 #include "attn_tc_work.cuh"
@@ -105,8 +107,11 @@ pod_tc_kernel(const __grid_constant__ CUtensorMap qmap_p, const __grid_constant_
       const int mi = sch.prefill_items_per_head - 1 - (int)(np0 % sch.prefill_items_per_head);
       const long long rem = np0 / sch.prefill_items_per_head;
       const int h = (int)(rem % pp.num_heads), b = (int)(rem / pp.num_heads);
-      if (sch.prefill_blocks == 2)
-        prefill2_work<T>(&qmap_p, &kmap_p, &vmap_p, &kt_p, &vt_p, pp, sm.u.prefill2, sm.bar, tmem, mi, h, b, true);
+      if (sch.prefill_blocks == 2) {
+        PrefillSegment seg{};
+        seg.mt2 = mi, seg.h = h, seg.b = b, seg.j0 = 0, seg.j1 = INT_MAX, seg.parts = 1;
+        prefill2_work<T>(&qmap_p, &kmap_p, &vmap_p, &kt_p, &vt_p, pp, sm.u.prefill2, sm.bar, tmem, seg, true);
+      }
       else
         prefill_work<T>(&qmap_p, &kmap_p, &vmap_p, &kt_p, &vt_p, pp, sm.u.prefill, sm.bar, tmem, mi, h, b, true);
     } else {

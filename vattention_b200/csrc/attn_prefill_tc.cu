@@ -16,7 +16,12 @@
 // The running max used for scaling is only advanced when a row's new max exceeds it by more than
 // 2^8 (lazy rescale): O then needs a TMEM read-modify-write for that warp, otherwise none.
 // Tiles above the causal diagonal are skipped; only diagonal / tail tiles are masked.
+#include <climits>
+#include <type_traits>
 #include <cstdlib>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 
 #include "attn_common.cuh"
 #include "sm100_ptx.cuh"
@@ -143,10 +148,195 @@ prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
   const int pairs = (p.num_m_tiles + 1) / 2;
-  // REGS: 384 threads x 168 registers at launch; inside prefill2_work the producer / MMA warpgroup
-  // drops to 56 and the two softmax warpgroups take 224 each (128 x 56 + 256 x 224 = 384 x 168)
-  prefill2_work<T, MODE>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem,
-                         pairs - 1 - blockIdx.x, blockIdx.y, blockIdx.z, false);
+  // MODE 1: 384 threads x 168 registers at launch; the producer / MMA warpgroup drops to 56 and the two
+  // softmax warpgroups take 224 each (128 x 56 + 256 x 224 = 384 x 168)
+  PrefillSegment seg{};
+  seg.mt2 = pairs - 1 - blockIdx.x, seg.h = blockIdx.y, seg.b = blockIdx.z;
+  seg.j0 = 0, seg.j1 = INT_MAX, seg.parts = 1;
+  if (warp < 4) {
+    if constexpr (MODE > 0) setmaxnreg_dec<56>();
+    prefill2_work<T, MODE, 1>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, seg, false);
+  } else {
+    if constexpr (MODE > 0) setmaxnreg_inc<224>();
+    prefill2_work<T, MODE, 2>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, seg, false);
+  }
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ---- stream-K persistent prefill ---------------------------------------------------------------
+// One CTA per SM.  Items = (row-block pair, q head, batch entry); an item with n visible key tiles
+// contributes max(1, n) virtual tiles.  The flattened tile space, ordered batch -> kv head -> pair
+// (heavy first) -> q head of the group -> key tile, is cut into equal ranges per CTA ON THE DEVICE
+// (lengths come from cache_seqlens), so all SMs finish together whatever the item count (the grid
+// kernel runs 256 items of chunk 2048 as 1.73 waves on 148 SMs; chunk 512 fills only 128), CTAs that
+// run at the same time share one kv head's K/V in L2, and a short chunk deep in a long context is
+// split along the keys.  An item cut by a range boundary is reduced by its last part to arrive
+// (prefill2_work).  Workspace: 2 partial slots per CTA.
+constexpr int kSkMaxEntries = 4096;  // (batch entry, pair) prefix kept in shared memory
+
+struct __align__(1024) PrefillSkSmem {
+  Prefill2Smem data;
+  TcBarriers bar;
+  uint32_t tmem_base;
+  int warp_sum[kPrefill2Threads / 32];
+  int prefix[kSkMaxEntries + 1];  // exclusive prefix of virtual tiles over (batch entry, pair rank)
+};
+
+struct PrefillSkArgs {
+  float* ws_o;
+  float* ws_ml;
+  int* arrive;   // one counter per CTA (the item that starts in that CTA's range and runs past its end)
+  int pairs;     // row-block pairs per (batch entry, head)
+};
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kPrefill2Threads, 1)
+prefill_sk_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                  const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap kmap_tail,
+                  const __grid_constant__ CUtensorMap vmap_tail, const PrefillParams p, const PrefillSkArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  PrefillSkSmem& sm =
+      *reinterpret_cast<PrefillSkSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pairs = a.pairs, E = p.batch * pairs;
+  auto entry_vt = [&](int e) {  // virtual tiles of (batch entry e / pairs, pair rank e % pairs), heavy first
+    const int b = e / pairs, mt2 = pairs - 1 - e % pairs;
+    const int lk = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + p.seqlen_new;
+    int m0[2], rows[2], nt[2];
+    prefill_pair_tiles(p, lk, mt2, m0, rows, nt);
+    return max(1, max(nt[0], nt[1]));
+  };
+  // ---- block-wide exclusive scan of the entries into shared memory
+  const int per = (E + kPrefill2Threads - 1) / kPrefill2Threads;
+  const int e0 = min(E, (int)threadIdx.x * per), e1 = min(E, e0 + per);
+  int mine = 0;
+  for (int e = e0; e < e1; e++) mine += entry_vt(e);
+  int incl = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) sm.warp_sum[warp] = incl;
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&qmap);
+    prefetch_tensormap(&kmap);
+    prefetch_tensormap(&vmap);
+    // every barrier word holds a live mbarrier from here on, so segments can inval + re-init
+    for (int s = 0; s < kMaxStages; s++) {
+      mbar_init(&sm.bar.full[s], 1);
+      mbar_init(&sm.bar.empty[s], 1);
+    }
+    mbar_init(&sm.bar.q_full, 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&sm.bar.s_full[i], 1);
+      mbar_init(&sm.bar.p_ready[i], 1);
+      mbar_init(&sm.bar.o_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&sm.tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  {
+    int run = incl - mine;
+    for (int w = 0; w < warp; w++) run += sm.warp_sum[w];
+    for (int e = e0; e < e1; e++) {
+      sm.prefix[e] = run;
+      run += entry_vt(e);
+    }
+    if (e1 == E && (e0 < E || threadIdx.x == 0)) sm.prefix[E] = run;
+  }
+  __syncthreads();
+  const uint32_t tmem = sm.tmem_base;
+  const int G = p.group, Hkv = p.num_heads / p.group;
+  StreamKPlan pl;
+  pl.total = (int64_t)sm.prefix[E] * p.num_heads;
+  pl.ctas = gridDim.x;
+  pl.q = pl.total / pl.ctas;
+  pl.r = (int)(pl.total % pl.ctas);
+  const int cta = blockIdx.x;
+  const int64_t lo = sk_range_begin(pl, cta);
+  const int64_t hi = lo + pl.q + (cta < pl.r ? 1 : 0);
+  auto walk = [&](auto role) {
+    constexpr int ROLE = decltype(role)::value;
+    // locate tile `lo`: batch entry, kv head, pair rank, q head of the group, key tile
+    int b = 0;
+    {
+      int l = 0, r = p.batch;  // largest b with num_heads * prefix[b * pairs] <= lo
+      while (r - l > 1) {
+        const int m = (l + r) / 2;
+        if ((int64_t)sm.prefix[m * pairs] * p.num_heads <= lo) l = m;
+        else r = m;
+      }
+      b = l;
+    }
+    int64_t rem = lo - (int64_t)sm.prefix[b * pairs] * p.num_heads;
+    const int Sb0 = sm.prefix[(b + 1) * pairs] - sm.prefix[b * pairs];
+    int hkv = (int)(rem / ((int64_t)G * Sb0));
+    rem -= (int64_t)hkv * G * Sb0;
+    int k = 0;
+    {
+      int l = 0, r = pairs;  // largest k with G * (prefix[b pairs + k] - prefix[b pairs]) <= rem
+      while (r - l > 1) {
+        const int m = (l + r) / 2;
+        if ((int64_t)(sm.prefix[b * pairs + m] - sm.prefix[b * pairs]) * G <= rem) l = m;
+        else r = m;
+      }
+      k = l;
+    }
+    rem -= (int64_t)(sm.prefix[b * pairs + k] - sm.prefix[b * pairs]) * G;
+    int vt = sm.prefix[b * pairs + k + 1] - sm.prefix[b * pairs + k];
+    int g = (int)(rem / vt);
+    int tile = (int)(rem - (int64_t)g * vt);
+    bool live = true;  // barriers were initialised above
+    for (int64_t x = lo; x < hi;) {
+      const int64_t item_start = x - tile, item_end = item_start + vt;
+      const int64_t seg_end = hi < item_end ? hi : item_end;
+      PrefillSegment seg{};
+      seg.mt2 = pairs - 1 - k, seg.h = hkv * G + g, seg.b = b;
+      seg.j0 = tile, seg.j1 = tile + (int)(seg_end - x);
+      const int first_cta = sk_cta_of(pl, item_start), last_cta = sk_cta_of(pl, item_end - 1);
+      seg.parts = last_cta - first_cta + 1;
+      seg.ws_o = a.ws_o, seg.ws_ml = a.ws_ml;
+      seg.my_slot = 2 * cta + (lo >= item_start ? 0 : 1);
+      seg.first_cta = first_cta, seg.item_start = item_start, seg.plan = pl;
+      seg.arrive = a.arrive + first_cta;
+      prefill2_work<T, MODE, ROLE>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, seg, live);
+      x = seg_end;
+      if (x == item_end) {  // next item: q head of the group -> pair -> kv head -> batch entry
+        tile = 0;
+        if (++g == G) {
+          g = 0;
+          if (++k == pairs) {
+            k = 0;
+            if (++hkv == Hkv) {
+              hkv = 0;
+              b++;
+            }
+          }
+          if (b < p.batch) vt = sm.prefix[b * pairs + k + 1] - sm.prefix[b * pairs + k];
+        }
+      } else {
+        tile += (int)(seg_end - x);  // not reached: a segment always ends at hi or at the item's end
+      }
+    }
+  };
+  if (lo < hi) {
+    // role split at the top level: each side's code is dominated by its own setmaxnreg
+    if (warp < 4) {
+      if constexpr (MODE > 0) setmaxnreg_dec<56>();
+      walk(std::integral_constant<int, 1>{});
+    } else {
+      if constexpr (MODE > 0) setmaxnreg_inc<224>();
+      walk(std::integral_constant<int, 2>{});
+    }
+  }
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
@@ -156,33 +346,44 @@ int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
+int* prefill_arrive_counters(cudaStream_t stream, size_t need) { return arrival_counters(stream, 1, need); }
+
 template <typename T>
-void launch_t(const vattn_fwd_params_t& p, cudaStream_t stream) {
+void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
   PrefillTcLaunch L;
   build_prefill_tc(p, &L);
   const int tslot = timing_begin(stream);
-  // two row blocks per CTA need enough (pair, head, batch) items to fill the SMs; short chunks
-  // keep one block per CTA
-  const long long pair_items = (long long)((L.pp.num_m_tiles + 1) / 2) * p.num_heads * p.batch;
+  const int pairs = (L.pp.num_m_tiles + 1) / 2;
+  const long long pair_items = (long long)pairs * p.num_heads * p.batch;
+  static const bool grid_forced = [] {
+    const char* e = std::getenv("VATTN_PREFILL_SCHED");
+    return e && std::string(e) == "grid";
+  }();
   if (t_pod_lean) {
     const size_t smem = sizeof(PrefillLeanKernelSmem) + 1024;
     VATTN_CUDA(cudaFuncSetAttribute(prefill_lean_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(L.pp.num_m_tiles, p.num_heads, p.batch);
     prefill_lean_tc_kernel<T><<<grid, kThreads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail, L.vmap_tail,
                                                                 L.pp);
+  } else if (p.seqlen_q > kBM && !grid_forced && (long long)p.batch * pairs <= kSkMaxEntries && ws) {
+    // stream-K persistent kernel: one CTA per SM, the work split computed on the device
+    const int ctas = num_sms();
+    PrefillSkArgs a;
+    a.pairs = pairs;
+    a.arrive = prefill_arrive_counters(stream, ctas);
+    a.ws_o = static_cast<float*>(ws);
+    a.ws_ml = a.ws_o + (size_t)2 * ctas * 2 * kBM * kD;
+    const size_t smem = sizeof(PrefillSkSmem) + 1024;
+    VATTN_CUDA(cudaFuncSetAttribute(prefill_sk_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prefill_sk_kernel<T, 1><<<ctas, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
+                                                                      L.vmap_tail, L.pp, a);
   } else if (p.seqlen_q > kBM && pair_items >= num_sms() && !env_int("VATTN_PREFILL_SINGLE", 0)) {
+    // two row blocks per CTA, one CTA per (pair, head, batch entry): needs enough items to fill the SMs
     const size_t smem = sizeof(Prefill2KernelSmem) + 1024;
-    dim3 grid((L.pp.num_m_tiles + 1) / 2, p.num_heads, p.batch);
-    // VATTN_PREFILL_REGS=1: S row read from TMEM once and kept in registers (setmaxnreg); =2: additionally
-    // one exponential in four on the FMA pipe (poly_exp2).  Written but not yet measured, hence opt-in
-    auto launch2 = [&](auto kernel) {
-      VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kernel<<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail, L.vmap_tail, L.pp);
-    };
-    const int mode = env_int("VATTN_PREFILL_REGS", 0);
-    if (mode == 2) launch2(prefill2_tc_kernel<T, 2>);
-    else if (mode == 1) launch2(prefill2_tc_kernel<T, 1>);
-    else launch2(prefill2_tc_kernel<T, 0>);
+    dim3 grid(pairs, p.num_heads, p.batch);
+    VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prefill2_tc_kernel<T, 1><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
+                                                                       L.vmap_tail, L.pp);
   } else {
     const size_t smem = sizeof(PrefillKernelSmem) + 1024;
     VATTN_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -249,11 +450,16 @@ bool prefill_tc_supported(const vattn_fwd_params_t& p, std::string* why) {
   return true;
 }
 
-size_t prefill_tc_workspace(const vattn_fwd_params_t&) { return 0; }
+size_t prefill_tc_workspace(const vattn_fwd_params_t& p) {
+  // stream-K: two partial slots per CTA, each [2 blocks][128 rows][128 + 2] fp32
+  if (p.seqlen_q <= kBM) return 0;
+  return (size_t)2 * num_sms() * 2 * kBM * (kD + 2) * sizeof(float);
+}
 
-void launch_prefill_tc(const vattn_fwd_params_t& p, void*, size_t, cudaStream_t stream) {
-  if (p.dtype == VATTN_DTYPE_BF16) launch_t<__nv_bfloat16>(p, stream);
-  else launch_t<__half>(p, stream);
+void launch_prefill_tc(const vattn_fwd_params_t& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (ws_bytes < prefill_tc_workspace(p)) ws = nullptr;  // (the POD fork passes its own carve-out)
+  if (p.dtype == VATTN_DTYPE_BF16) launch_t<__nv_bfloat16>(p, ws, stream);
+  else launch_t<__half>(p, ws, stream);
 }
 
 }  // namespace vattn

@@ -69,6 +69,7 @@ struct TcBarriers {
   uint64_t q_full;                               // prefill: Q block landed
   uint64_t s_full[2], p_ready[2];                // S ready for softmax / P ready for the PV MMA
   uint64_t o_full[2];                            // decode: O_j^T ready; prefill uses [0] as "PV_j done"
+  int ticket;                                    // split items: arrival order of this part (prefill stream-K)
 };
 
 // ======================================================================== decode ====
@@ -421,18 +422,43 @@ __device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap,
       if (p.arrive && sm.ticket == seg.parts - 1) {
         __threadfence();
         write_out = true;
+        const int np = seg.parts;
+        // The ring is idle here (every staged tile was consumed before the last O^T was read): stage
+        // all (head, part) statistics in it with ONE round of independent loads, so the reduction is
+        // not a chain of dependent L2 round trips (19 parts x 8 heads at B16 x 32K: ~45 us as a chain)
+        float* st_m = reinterpret_cast<float*>(sm.ring[0]);
+        float* st_l = st_m + G * np;
+        const bool staged = (size_t)2 * G * np * sizeof(float) <= (size_t)STAGES * kTileBytes;
+        if (staged) {
+          for (int idx = t; idx < G * np; idx += 128) {
+            const int g = idx / np, c = idx - g * np;
+            const int64_t base = seg.red_idx + g * seg.red_stride_g + c * seg.red_stride_c;
+            st_m[idx] = __ldcg(p.ws_ml + base * 2);
+            st_l[idx] = __ldcg(p.ws_ml + base * 2 + 1);
+          }
+          named_bar_sync(1, 128);
+        }
 #pragma unroll
         for (int g = 0; g < GP; g++) {
           if (g >= G) continue;
           const int64_t base = seg.red_idx + g * seg.red_stride_g;
           float M = -INFINITY;
-          for (int c = 0; c < seg.parts; c++) M = fmaxf(M, __ldcg(p.ws_ml + (base + c * seg.red_stride_c) * 2));
+          if (staged) {
+            for (int c = 0; c < np; c++) M = fmaxf(M, st_m[g * np + c]);
+          } else {
+            for (int c = 0; c < np; c++) M = fmaxf(M, __ldcg(p.ws_ml + (base + c * seg.red_stride_c) * 2));
+          }
           float o = 0.f, L = 0.f;
-          for (int c = 0; c < seg.parts; c++) {
+#pragma unroll 4
+          for (int c = 0; c < np; c++) {
             const int64_t idx = base + c * seg.red_stride_c;
-            const float w = fast_exp2(__ldcg(p.ws_ml + idx * 2) - M);
-            L = fmaf(__ldcg(p.ws_ml + idx * 2 + 1), w, L);
-            o = fmaf(__ldcg(p.ws_acc + idx * kHeadDim + t), w, o);
+            const float lc = staged ? st_l[g * np + c] : __ldcg(p.ws_ml + idx * 2 + 1);
+            const float mc = staged ? st_m[g * np + c] : __ldcg(p.ws_ml + idx * 2);
+            // an empty part (l == 0) never wrote its accumulator row: do not read it (0 * garbage)
+            const float w = lc > 0.f ? fast_exp2(mc - M) : 0.f;
+            const float a = lc > 0.f ? __ldcg(p.ws_acc + idx * kHeadDim + t) : 0.f;
+            L = fmaf(lc, w, L);
+            o = fmaf(a, w, o);
           }
           acc[g] = o, Lg[g] = L, m_run[g] = M;
         }
@@ -907,6 +933,13 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
 // TMEM: S0 | S1 | O0 | O1 (128 columns each); P_t is written in place over the first 64 columns of
 // S_t (16-bit packed) once they have been consumed, and the next QK^T into S_t is issued after
 // PV_t in program order (tcgen05.mma executes in issue order).
+//
+// One call handles key tiles [j0, j1) of one item (row-block pair, q head, batch entry).  The grid
+// kernel passes the whole range; the stream-K kernel (attn_prefill_tc.cu) cuts the flattened
+// (item, key tile) space into equal ranges per persistent CTA, so an item may be split into `parts`
+// segments: each publishes its un-normalised (O, m, l) and the last one to arrive reduces them
+// (the role of FA-2's split-KV kernel + combine, flash_fwd_kernel.h:503-1077,1115+, which the
+// reference needs for short chunks deep in a long context, flash_api.cpp:258-323).
 constexpr int kPrefill2Threads = 384;
 constexpr int kPrefill2Stages = 4;
 constexpr uint32_t kCol2S = 0, kCol2O = 256;  // S_t at kCol2S + 128 t, O_t at kCol2O + 128 t
@@ -916,32 +949,64 @@ struct __align__(1024) Prefill2Smem {
   uint8_t ring[kPrefill2Stages][kTileBytes];
 };
 
-template <typename T, int MODE = 0>
+struct PrefillSegment {
+  int mt2, h, b;       // row-block pair, q head, batch entry
+  int j0, j1;          // key tiles [j0, j1) of the item (clamped to what each block can see)
+  int parts;           // segments the item is split into; 1: this call writes the final result
+  // ---- parts > 1 only
+  float* ws_o;         // [slot][2 blocks][128 rows][128] fp32, un-normalised
+  float* ws_ml;        // [slot][2 blocks][128 rows][2]   (reference max in the log2 domain, row sum)
+  int my_slot;
+  int first_cta;       // the parts are the CTAs first_cta .. first_cta + parts - 1
+  int64_t item_start;  // flattened index of the item's tile 0 (to recompute the other parts' slots)
+  StreamKPlan plan;
+  int* arrive;         // arrival counter of this item (zero before and after the launch)
+};
+
+// number of key tiles row block (2 mt2 + t) can see: nt[t]; rows[t] valid query rows; m0[t] first row
+__device__ __forceinline__ void prefill_pair_tiles(const PrefillParams& p, int lk, int mt2, int (&m0)[2],
+                                                   int (&rows)[2], int (&nt)[2]) {
+  const int shift = lk - p.seqlen_q;
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    m0[t] = (mt2 * 2 + t) * kTile;
+    rows[t] = min(kTile, p.seqlen_q - m0[t]);
+    int kv_end = lk;
+    if (p.causal) kv_end = min(lk, m0[t] + rows[t] + shift);
+    if (kv_end < 0 || rows[t] <= 0) kv_end = 0;
+    nt[t] = (kv_end + kTile - 1) / kTile;
+  }
+}
+
+// MODE 0: the S row is read from TMEM twice (max pass, exp pass).  MODE 1: read once and kept in
+// registers for both passes (~224 registers per softmax thread).
+// ROLE 0: the whole CTA calls the function (POD kernel).  ROLE 1 / 2: the caller has split the roles
+// at the top level -- warps 0-3 call <ROLE 1> (TMA producer, MMA issuer), warps 4-11 call <ROLE 2>
+// (softmax) -- so that each side's code is dominated by its own setmaxnreg (ptxas allocates
+// registers per setmaxnreg region) and a persistent loop executes setmaxnreg once.  The CTA-wide
+// barriers are explicit bar.sync 3, 384, which both sides reach from their own code.
+__device__ __forceinline__ void cta_sync_384() { named_bar_sync(3, kPrefill2Threads); }
+
+template <typename T, int MODE = 0, int ROLE = 0>
 __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
                               const CUtensorMap* kmap_tail, const CUtensorMap* vmap_tail,
                               const PrefillParams& p, Prefill2Smem& sm, TcBarriers& bar, uint32_t tmem,
-                              int mt2, int h, int b, bool barriers_live) {
+                              const PrefillSegment& seg, bool barriers_live) {
   constexpr int kStages = kPrefill2Stages;
   constexpr int kBM = kTile, kBN = kTile, kD = kHeadDim;
-  const int hkv = h / p.group;
   constexpr bool REGS = MODE > 0;
-  constexpr int POLY = MODE == 2 ? 4 : 0;
+  const int h = seg.h, b = seg.b;
+  const int hkv = h / p.group;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = p.cache_batch_idx ? p.cache_batch_idx[b] : b;
   const int lk = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + p.seqlen_new;
   const int shift = lk - p.seqlen_q;
-  // per block t: first row, valid rows, number of key tiles
-  int m0[2], rows[2], nt[2];
+  int m0[2], rows[2], nt[2], nl[2];
+  prefill_pair_tiles(p, lk, seg.mt2, m0, rows, nt);
+  const int j0 = seg.j0;
 #pragma unroll
-  for (int t = 0; t < 2; t++) {
-    m0[t] = (mt2 * 2 + t) * kBM;
-    rows[t] = min(kBM, p.seqlen_q - m0[t]);
-    int kv_end = lk;
-    if (p.causal) kv_end = min(lk, m0[t] + rows[t] + shift);
-    if (kv_end < 0 || rows[t] <= 0) kv_end = 0;
-    nt[t] = (kv_end + kBN - 1) / kBN;
-  }
-  const int n = max(nt[0], nt[1]);  // key tiles to stage (block 1 sees at least as many as block 0)
+  for (int t = 0; t < 2; t++) nl[t] = max(0, min(seg.j1, nt[t]) - j0);  // local tile count of block t
+  const int n = max(nl[0], nl[1]);                                      // key tiles to stage
 
   if (threadIdx.x == 0) {
     mbar_reinit(&bar.q_full, 1, barriers_live);
@@ -956,11 +1021,10 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
     }
     fence_mbar_init();
   }
-  __syncthreads();
+  cta_sync_384();
 
-  // role split by warpgroup first, so that (REGS) each setmaxnreg dominates its role's code
-  if (warp < 4) {
-  if constexpr (REGS) setmaxnreg_dec<56>();
+  if constexpr (ROLE != 2) {
+  if (ROLE == 1 || warp < 4) {
   if (warp == 0) {
     // =========================================================== TMA producer ====
     if (lane == 0 && n > 0) {
@@ -973,7 +1037,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         const int s = pos % kStages;
         mbar_wait(&bar.empty[s], ((pos / kStages) & 1) ^ 1);
         load_kv_tile(sm.ring[s], (pos & 1) ? vmap : kmap, (pos & 1) ? vmap_tail : kmap_tail, &bar.full[s],
-                     (pos >> 1) * kBN, hkv, slot, safe_rows, p.tail_rows);
+                     (j0 + (pos >> 1)) * kBN, hkv, slot, safe_rows, p.tail_rows);
       }
     }
   } else if (warp == 1) {
@@ -985,7 +1049,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         tc_fence_after();
         return smem_u32(sm.ring[pos % kStages]);
       };
-      auto issue_qk = [&](int t, int j, uint32_t k0) {
+      auto issue_qk = [&](int t, uint32_t k0) {
         const uint32_t q_addr = smem_u32(sm.q[t]);
 #pragma unroll
         for (int ks = 0; ks < kD / 16; ks++) {
@@ -1008,8 +1072,8 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       // prologue: S_t(0) for both blocks
       {
         const uint32_t k0 = wait_slot(0);
-        if (nt[0] > 0) issue_qk(0, 0, k0);
-        if (nt[1] > 0) issue_qk(1, 0, k0);
+        if (nl[0] > 0) issue_qk(0, k0);
+        if (nl[1] > 0) issue_qk(1, k0);
         umma_commit(&bar.empty[0]);
       }
       for (int j = 0; j < n; j++) {
@@ -1017,29 +1081,31 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         uint32_t k1 = 0;
         const bool more = j + 1 < n;
         // block 0: PV(j) then the next QK^T, which overwrites S0/P0 only after PV0(j) in order
-        if (j < nt[0]) issue_pv(0, j, v0);
+        if (j < nl[0]) issue_pv(0, j, v0);
         if (more) {
           k1 = wait_slot(2 * j + 2);
-          if (j + 1 < nt[0]) issue_qk(0, j + 1, k1);
+          if (j + 1 < nl[0]) issue_qk(0, k1);
         }
-        if (j < nt[1]) issue_pv(1, j, v0);
+        if (j < nl[1]) issue_pv(1, j, v0);
         umma_commit(&bar.empty[(2 * j + 1) % kStages]);  // V_j consumed by both blocks
         if (more) {
-          if (j + 1 < nt[1]) issue_qk(1, j + 1, k1);
+          if (j + 1 < nl[1]) issue_qk(1, k1);
           umma_commit(&bar.empty[(2 * j + 2) % kStages]);  // K_{j+1} consumed by both blocks
         }
       }
     }
   }
-  } else {
+  }
+  }
+  if constexpr (ROLE != 1) {
+  if (ROLE == 2 || warp >= 4) {
     // ==================================================== softmax / epilogue ====
-    if constexpr (REGS) setmaxnreg_inc<224>();
     const int t = (warp - 4) >> 2;            // which row block this warpgroup owns
     const int i = (threadIdx.x - 128) & 127;  // query row inside the block == TMEM lane
     const int sw = warp & 3;
     const uint32_t lane_base = (uint32_t)(sw * 32) << 16;
     const int qi = m0[t] + i;
-    const int my_n = nt[t];
+    const int my_n = nl[t];
     int limit = lk - 1;
     if (p.causal) limit = min(limit, qi + shift);
     float m_ref = -INFINITY, l = 0.f;
@@ -1049,7 +1115,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
     for (int j = 0; j < my_n; j++) {
       mbar_wait(&bar.s_full[t], j & 1);
       tc_fence_after();
-      const int key0 = j * kBN;
+      const int key0 = (j0 + j) * kBN;
       const bool need_mask = key0 + kBN - 1 > limit;
       const bool warp_mask = __any_sync(0xffffffffu, need_mask);
       uint32_t s0[REGS ? 32 : 1], s1[REGS ? 32 : 1], s2[REGS ? 32 : 1], s3[REGS ? 32 : 1];
@@ -1099,19 +1165,19 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t packed[32];
         if (warp_mask) {
-          regs_quarter_exp<T, true, POLY>(s0, packed, p.scale_log2, mref_safe, key0, limit, ls);
-          regs_quarter_exp<T, true, POLY>(s1, packed + 16, p.scale_log2, mref_safe, key0 + 32, limit, ls);
+          regs_quarter_exp<T, true, 0>(s0, packed, p.scale_log2, mref_safe, key0, limit, ls);
+          regs_quarter_exp<T, true, 0>(s1, packed + 16, p.scale_log2, mref_safe, key0 + 32, limit, ls);
         } else {
-          regs_quarter_exp<T, false, POLY>(s0, packed, p.scale_log2, mref_safe, 0, 0, ls);
-          regs_quarter_exp<T, false, POLY>(s1, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false, 0>(s0, packed, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false, 0>(s1, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
         }
         tmem_st_x32(s_addr, packed);  // keys 0..63 of P_t(j), 2 per column
         if (warp_mask) {
-          regs_quarter_exp<T, true, POLY>(s2, packed, p.scale_log2, mref_safe, key0 + 64, limit, ls);
-          regs_quarter_exp<T, true, POLY>(s3, packed + 16, p.scale_log2, mref_safe, key0 + 96, limit, ls);
+          regs_quarter_exp<T, true, 0>(s2, packed, p.scale_log2, mref_safe, key0 + 64, limit, ls);
+          regs_quarter_exp<T, true, 0>(s3, packed + 16, p.scale_log2, mref_safe, key0 + 96, limit, ls);
         } else {
-          regs_quarter_exp<T, false, POLY>(s2, packed, p.scale_log2, mref_safe, 0, 0, ls);
-          regs_quarter_exp<T, false, POLY>(s3, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false, 0>(s2, packed, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false, 0>(s3, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
         }
         tmem_st_x32(s_addr + 32, packed);  // keys 64..127
         l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
@@ -1120,7 +1186,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
                        : tile_exp_store<T, false>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit);
       }
       tmem_wait_st();
-      if ((j + 1) * kBN > lk) {
+      if ((j0 + j + 1) * kBN > lk) {
         const int pv = 2 * j + 1;
         mbar_wait(&bar.full[pv % kStages], (pv / kStages) & 1);
         // both warpgroups may reach the tail tile: zeroing the same rows twice is harmless
@@ -1142,36 +1208,116 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       mbar_wait(&bar.o_full[t], (my_n - 1) & 1);  // phases <= my_n-2 are known complete (see above)
       tc_fence_after();
     }
-    const float inv = l > 0.f ? 1.f / l : 0.f;
     char* orow = p.out + b * p.o_b + (int64_t)qi * p.o_r + (int64_t)h * p.o_h;
+    if (seg.parts == 1) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
 #pragma unroll
-    for (int c = 0; c < kD; c += 32) {
-      uint32_t r[32];
-      if (my_n > 0) {
-        tmem_ld_x32(o_addr + c, r);
-        tmem_wait_ld();
-      } else {
+      for (int c = 0; c < kD; c += 32) {
+        uint32_t r[32];
+        if (my_n > 0) {
+          tmem_ld_x32(o_addr + c, r);
+          tmem_wait_ld();
+        } else {
 #pragma unroll
-        for (int e = 0; e < 32; e++) r[e] = 0;
-      }
-      if (i < rows[t]) {
+          for (int e = 0; e < 32; e++) r[e] = 0;
+        }
+        if (i < rows[t]) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 8) {
-          uint4 o;
-          o.x = Elem<T>::from_f2(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
-          o.y = Elem<T>::from_f2(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
-          o.z = Elem<T>::from_f2(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
-          o.w = Elem<T>::from_f2(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + (c + e) * 2) = o;
+          for (int e = 0; e < 32; e += 8) {
+            uint4 o;
+            o.x = Elem<T>::from_f2(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+            o.y = Elem<T>::from_f2(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
+            o.z = Elem<T>::from_f2(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
+            o.w = Elem<T>::from_f2(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + (c + e) * 2) = o;
+          }
         }
       }
+      if (p.lse && i < rows[t])
+        p.lse[((int64_t)b * p.num_heads + h) * p.seqlen_q + qi] =
+            l > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : INFINITY;
+    } else {
+      // ---- split item: publish this part, the last part to arrive reduces all of them ----
+      const int64_t mine = ((int64_t)seg.my_slot * 2 + t) * kBM + i;
+      seg.ws_ml[mine * 2] = m_ref;
+      seg.ws_ml[mine * 2 + 1] = l;
+      if (my_n > 0) {
+        float* dst = seg.ws_o + mine * kD;
+#pragma unroll
+        for (int c = 0; c < kD; c += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(o_addr + c, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<uint4*>(dst + c + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        }
+      }
+      named_bar_sync(2, 256);  // both softmax warpgroups have stored their rows
+      if (threadIdx.x == 128) {
+        __threadfence();       // cumulative: orders the other threads' stores before the ticket
+        bar.ticket = atomicAdd(seg.arrive, 1);
+      }
+      named_bar_sync(2, 256);
+      if (bar.ticket == seg.parts - 1) {
+        __threadfence();
+        float M = -INFINITY;
+        for (int c = 0; c < seg.parts; c++) {
+          const int cta = seg.first_cta + c;
+          const int64_t sl = 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+          M = fmaxf(M, __ldcg(seg.ws_ml + ((sl * 2 + t) * kBM + i) * 2));
+        }
+        const float Ms = (M == -INFINITY) ? 0.f : M;
+        float L = 0.f;
+        for (int c = 0; c < seg.parts; c++) {
+          const int cta = seg.first_cta + c;
+          const int64_t sl = 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+          const int64_t row = (sl * 2 + t) * kBM + i;
+          const float lc = __ldcg(seg.ws_ml + row * 2 + 1);
+          if (lc > 0.f) L = fmaf(lc, fast_exp2(__ldcg(seg.ws_ml + row * 2) - Ms), L);
+        }
+        const float inv = L > 0.f ? 1.f / L : 0.f;
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {  // 64 columns at a time: 64 accumulator registers
+          float acc[kD / 2];
+#pragma unroll
+          for (int e = 0; e < kD / 2; e++) acc[e] = 0.f;
+          for (int c = 0; c < seg.parts; c++) {
+            const int cta = seg.first_cta + c;
+            const int64_t sl = 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+            const int64_t row = (sl * 2 + t) * kBM + i;
+            if (!(__ldcg(seg.ws_ml + row * 2 + 1) > 0.f)) continue;  // empty part: its O row was never written
+            const float w = fast_exp2(__ldcg(seg.ws_ml + row * 2) - Ms);
+            const float4* src = reinterpret_cast<const float4*>(seg.ws_o + row * kD + half * (kD / 2));
+#pragma unroll
+            for (int e = 0; e < kD / 8; e++) {
+              const float4 v = __ldcg(src + e);
+              acc[4 * e] = fmaf(v.x, w, acc[4 * e]), acc[4 * e + 1] = fmaf(v.y, w, acc[4 * e + 1]);
+              acc[4 * e + 2] = fmaf(v.z, w, acc[4 * e + 2]), acc[4 * e + 3] = fmaf(v.w, w, acc[4 * e + 3]);
+            }
+          }
+          if (i < rows[t]) {
+#pragma unroll
+            for (int e = 0; e < kD / 2; e += 8) {
+              uint4 o;
+              o.x = Elem<T>::from_f2(acc[e] * inv, acc[e + 1] * inv);
+              o.y = Elem<T>::from_f2(acc[e + 2] * inv, acc[e + 3] * inv);
+              o.z = Elem<T>::from_f2(acc[e + 4] * inv, acc[e + 5] * inv);
+              o.w = Elem<T>::from_f2(acc[e + 6] * inv, acc[e + 7] * inv);
+              *reinterpret_cast<uint4*>(orow + (half * (kD / 2) + e) * 2) = o;
+            }
+          }
+        }
+        if (p.lse && i < rows[t])
+          p.lse[((int64_t)b * p.num_heads + h) * p.seqlen_q + qi] =
+              L > 0.f ? (M + log2f(L)) * 0.6931471805599453f : INFINITY;
+        if (threadIdx.x == 128) *seg.arrive = 0;  // ready for the next launch
+      }
     }
-    if (p.lse && i < rows[t])
-      p.lse[((int64_t)b * p.num_heads + h) * p.seqlen_q + qi] =
-          l > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : INFINITY;
+  }
   }
   tc_fence_before();
-  __syncthreads();
+  cta_sync_384();
 }
 
 }  // namespace tcwork

@@ -55,6 +55,59 @@ struct TimingState {
 
 thread_local bool t_pod_lean = false;  // attn_tc_host.h
 
+// ---- arrival counters (attn_common.cuh) ---------------------------------------------------------
+namespace {
+constexpr size_t kCounterSliceInts = 1 << 16;
+constexpr int kCounterSlices = 32;
+struct CounterPool {
+  int* base = nullptr;
+  int next = 0;
+  std::unordered_map<uint64_t, int*> slices;
+};
+std::mutex g_counter_mu;
+std::unordered_map<int, CounterPool> g_counter_pools;  // per device
+
+int* zeroed_ints(size_t n) {
+  // may run while the calling thread's stream is being captured: allocate and clear off to the side
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  VATTN_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
+  int* ptr = nullptr;
+  cudaError_t e = cudaMalloc(&ptr, n * sizeof(int));
+  if (e == cudaSuccess) {
+    cudaStream_t side;
+    e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+      e = cudaMemsetAsync(ptr, 0, n * sizeof(int), side);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(side);
+      cudaStreamDestroy(side);
+    }
+  }
+  cudaThreadExchangeStreamCaptureMode(&mode);
+  cuda_check(e, "arrival counter allocation");
+  return ptr;
+}
+}  // namespace
+
+int* arrival_counters(cudaStream_t stream, int user, size_t need) {
+  int dev = 0;
+  VATTN_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(g_counter_mu);
+  CounterPool& pool = g_counter_pools[dev];
+  const uint64_t key = (reinterpret_cast<uint64_t>(stream) << 2) ^ (uint64_t)user;
+  auto it = pool.slices.find(key);
+  if (it != pool.slices.end() && need <= kCounterSliceInts) return it->second;
+  if (need > kCounterSliceInts || pool.next >= kCounterSlices) {
+    // oversized request or more (stream, user) pairs than slices: a dedicated, never freed block
+    int* big = zeroed_ints(need > kCounterSliceInts ? need : kCounterSliceInts);
+    pool.slices[key] = big;
+    return big;
+  }
+  if (!pool.base) pool.base = zeroed_ints(kCounterSliceInts * kCounterSlices);
+  int* slice = pool.base + (size_t)pool.next++ * kCounterSliceInts;
+  pool.slices[key] = slice;
+  return slice;
+}
+
 int timing_begin(cudaStream_t stream) {
   std::lock_guard<std::mutex> g(g_timing.mu);
   if (!g_timing.enabled) return -1;
