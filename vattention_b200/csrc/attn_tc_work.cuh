@@ -1093,6 +1093,9 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
           umma_commit(&bar.empty[(2 * j + 2) % kStages]);  // K_{j+1} consumed by both blocks
         }
       }
+      // the last commit (V_{n-1}'s slot) is observed by nobody else: wait for it here, so that no
+      // asynchronous arrival is still in flight when a persistent caller re-initialises the barriers
+      mbar_wait(&bar.empty[(2 * n - 1) % kStages], ((2 * n - 1) / kStages) & 1);
     }
   }
   }
