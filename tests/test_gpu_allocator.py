@@ -277,7 +277,7 @@ def test_map_common_pages_alias_on_the_real_driver():
     lens = torch.full((B,), n, dtype=torch.int32, device="cuda")
     out = att.flash_attn_with_kvcache(q, ts[0][:, :n], ts[L][:, :n], cache_seqlens=lens, causal=True)
     torch.cuda.synchronize()
-    assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])
+    assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])   # same bytes, same schedule, same bits
     want = ref.attn_with_kvcache_ref(q[:1].cpu(), ts[0][:1, :n].cpu(), ts[L][:1, :n].cpu(),
                                      cache_seqlens=lens[:1].cpu(), causal=True)
     err = (out[:1].float().cpu() - want.float()).abs().max().item()

@@ -31,6 +31,8 @@
 
 namespace vattn {
 
+size_t prefill_tc_workspace(const vattn_fwd_params_t& p);
+
 namespace {
 
 using namespace ptx;
@@ -166,13 +168,15 @@ prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
 
 // ---- stream-K persistent prefill ---------------------------------------------------------------
 // One CTA per SM.  Items = (row-block pair, q head, batch entry); an item with n visible key tiles
-// contributes max(1, n) virtual tiles.  The flattened tile space, ordered batch -> kv head -> pair
-// (heavy first) -> q head of the group -> key tile, is cut into equal ranges per CTA ON THE DEVICE
-// (lengths come from cache_seqlens), so all SMs finish together whatever the item count (the grid
-// kernel runs 256 items of chunk 2048 as 1.73 waves on 148 SMs; chunk 512 fills only 128), CTAs that
-// run at the same time share one kv head's K/V in L2, and a short chunk deep in a long context is
-// split along the keys.  An item cut by a range boundary is reduced by its last part to arrive
-// (prefill2_work).  Workspace: 2 partial slots per CTA.
+// contributes max(1, n) virtual tiles.  Per (batch entry, kv head) group, the flattened tile space,
+// ordered pair (heavy first) -> q head of the group -> key tile, is cut into equal ranges per CTA ON
+// THE DEVICE (lengths come from cache_seqlens), so all SMs finish a group together whatever the item
+// count (the grid kernel runs 256 items of chunk 2048 as 1.73 waves on 148 SMs; chunk 512 fills only
+// 128), all CTAs stream the same kv head's K/V at any moment (L2 resident), and a short chunk deep in
+// a long context is split along the keys.  An item cut by a range boundary is reduced by its last
+// part to arrive (prefill2_work).  Workspace: 2 partial slots per (group, CTA).
+// (First version: equal ranges over the whole launch -- measured 898 vs 986 TFLOP/s for the grid
+// kernel at chunk 2048: all four kv heads, 256 MB of K/V, were in flight at once.)
 constexpr int kSkMaxEntries = 4096;  // (batch entry, pair) prefix kept in shared memory
 
 struct __align__(1024) PrefillSkSmem {
@@ -255,87 +259,70 @@ prefill_sk_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constan
   __syncthreads();
   const uint32_t tmem = sm.tmem_base;
   const int G = p.group, Hkv = p.num_heads / p.group;
-  StreamKPlan pl;
-  pl.total = (int64_t)sm.prefix[E] * p.num_heads;
-  pl.ctas = gridDim.x;
-  pl.q = pl.total / pl.ctas;
-  pl.r = (int)(pl.total % pl.ctas);
-  const int cta = blockIdx.x;
-  const int64_t lo = sk_range_begin(pl, cta);
-  const int64_t hi = lo + pl.q + (cta < pl.r ? 1 : 0);
+  const int cta = blockIdx.x, ctas = gridDim.x;
+  // One (batch entry, kv head) group at a time, its G x pairs items cut into equal ranges per CTA:
+  // every SM streams the SAME kv head's K/V at any moment (64 MB at 128K context: L2 resident),
+  // whereas equal ranges over the whole launch would put all kv heads in flight at once.
   auto walk = [&](auto role) {
     constexpr int ROLE = decltype(role)::value;
-    // locate tile `lo`: batch entry, kv head, pair rank, q head of the group, key tile
-    int b = 0;
-    {
-      int l = 0, r = p.batch;  // largest b with num_heads * prefix[b * pairs] <= lo
-      while (r - l > 1) {
-        const int m = (l + r) / 2;
-        if ((int64_t)sm.prefix[m * pairs] * p.num_heads <= lo) l = m;
-        else r = m;
-      }
-      b = l;
-    }
-    int64_t rem = lo - (int64_t)sm.prefix[b * pairs] * p.num_heads;
-    const int Sb0 = sm.prefix[(b + 1) * pairs] - sm.prefix[b * pairs];
-    int hkv = (int)(rem / ((int64_t)G * Sb0));
-    rem -= (int64_t)hkv * G * Sb0;
-    int k = 0;
-    {
-      int l = 0, r = pairs;  // largest k with G * (prefix[b pairs + k] - prefix[b pairs]) <= rem
-      while (r - l > 1) {
-        const int m = (l + r) / 2;
-        if ((int64_t)(sm.prefix[b * pairs + m] - sm.prefix[b * pairs]) * G <= rem) l = m;
-        else r = m;
-      }
-      k = l;
-    }
-    rem -= (int64_t)(sm.prefix[b * pairs + k] - sm.prefix[b * pairs]) * G;
-    int vt = sm.prefix[b * pairs + k + 1] - sm.prefix[b * pairs + k];
-    int g = (int)(rem / vt);
-    int tile = (int)(rem - (int64_t)g * vt);
     bool live = true;  // barriers were initialised above
-    for (int64_t x = lo; x < hi;) {
-      const int64_t item_start = x - tile, item_end = item_start + vt;
-      const int64_t seg_end = hi < item_end ? hi : item_end;
-      PrefillSegment seg{};
-      seg.mt2 = pairs - 1 - k, seg.h = hkv * G + g, seg.b = b;
-      seg.j0 = tile, seg.j1 = tile + (int)(seg_end - x);
-      const int first_cta = sk_cta_of(pl, item_start), last_cta = sk_cta_of(pl, item_end - 1);
-      seg.parts = last_cta - first_cta + 1;
-      seg.ws_o = a.ws_o, seg.ws_ml = a.ws_ml;
-      seg.my_slot = 2 * cta + (lo >= item_start ? 0 : 1);
-      seg.first_cta = first_cta, seg.item_start = item_start, seg.plan = pl;
-      seg.arrive = a.arrive + first_cta;
-      prefill2_work<T, MODE, ROLE>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, seg, live);
-      x = seg_end;
-      if (x == item_end) {  // next item: q head of the group -> pair -> kv head -> batch entry
+    for (int gi = 0; gi < p.batch * Hkv; gi++) {
+      const int b = gi / Hkv, hkv = gi - b * Hkv;
+      const int* pre = sm.prefix + b * pairs;  // pre[k] - pre[0]: virtual tiles of pair ranks < k
+      StreamKPlan pl;
+      pl.total = (int64_t)(pre[pairs] - pre[0]) * G;
+      pl.ctas = ctas;
+      pl.q = pl.total / ctas;
+      pl.r = (int)(pl.total % ctas);
+      const int64_t lo = sk_range_begin(pl, cta);
+      const int64_t hi = lo + pl.q + (cta < pl.r ? 1 : 0);
+      if (lo >= hi) continue;
+      // locate tile `lo`: pair rank, q head of the group, key tile
+      int k = 0;
+      {
+        int l = 0, r = pairs;  // largest k with G * (pre[k] - pre[0]) <= lo
+        while (r - l > 1) {
+          const int m = (l + r) / 2;
+          if ((int64_t)(pre[m] - pre[0]) * G <= lo) l = m;
+          else r = m;
+        }
+        k = l;
+      }
+      int64_t rem = lo - (int64_t)(pre[k] - pre[0]) * G;
+      int vt = pre[k + 1] - pre[k];
+      int g = (int)(rem / vt);
+      int tile = (int)(rem - (int64_t)g * vt);
+      for (int64_t x = lo; x < hi;) {
+        const int64_t item_start = x - tile, item_end = item_start + vt;
+        const int64_t seg_end = hi < item_end ? hi : item_end;
+        PrefillSegment seg{};
+        seg.mt2 = pairs - 1 - k, seg.h = hkv * G + g, seg.b = b;
+        seg.j0 = tile, seg.j1 = tile + (int)(seg_end - x);
+        const int first_cta = sk_cta_of(pl, item_start), last_cta = sk_cta_of(pl, item_end - 1);
+        seg.parts = last_cta - first_cta + 1;
+        seg.ws_o = a.ws_o, seg.ws_ml = a.ws_ml;
+        seg.slot_base = (int64_t)gi * ctas * 2;  // every group has its own slots: no reuse hazard
+        seg.my_slot = seg.slot_base + 2 * cta + (lo >= item_start ? 0 : 1);
+        seg.first_cta = first_cta, seg.item_start = item_start, seg.plan = pl;
+        seg.arrive = a.arrive + (int64_t)gi * ctas + first_cta;
+        prefill2_work<T, MODE, ROLE>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, seg, live);
+        x = seg_end;  // a segment ends at hi or at its item's end
         tile = 0;
         if (++g == G) {
           g = 0;
-          if (++k == pairs) {
-            k = 0;
-            if (++hkv == Hkv) {
-              hkv = 0;
-              b++;
-            }
-          }
-          if (b < p.batch) vt = sm.prefix[b * pairs + k + 1] - sm.prefix[b * pairs + k];
+          k++;
+          if (k < pairs) vt = pre[k + 1] - pre[k];
         }
-      } else {
-        tile += (int)(seg_end - x);  // not reached: a segment always ends at hi or at the item's end
       }
     }
   };
-  if (lo < hi) {
-    // role split at the top level: each side's code is dominated by its own setmaxnreg
-    if (warp < 4) {
-      if constexpr (MODE > 0) setmaxnreg_dec<56>();
-      walk(std::integral_constant<int, 1>{});
-    } else {
-      if constexpr (MODE > 0) setmaxnreg_inc<224>();
-      walk(std::integral_constant<int, 2>{});
-    }
+  // role split at the top level: each side's code is dominated by its own setmaxnreg
+  if (warp < 4) {
+    if constexpr (MODE > 0) setmaxnreg_dec<56>();
+    walk(std::integral_constant<int, 1>{});
+  } else {
+    if constexpr (MODE > 0) setmaxnreg_inc<224>();
+    walk(std::integral_constant<int, 2>{});
   }
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
@@ -365,18 +352,25 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
     dim3 grid(L.pp.num_m_tiles, p.num_heads, p.batch);
     prefill_lean_tc_kernel<T><<<grid, kThreads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail, L.vmap_tail,
                                                                 L.pp);
-  } else if (p.seqlen_q > kBM && !grid_forced && (long long)p.batch * pairs <= kSkMaxEntries && ws) {
+  } else if (p.seqlen_q > kBM && !grid_forced && (long long)p.batch * pairs <= kSkMaxEntries && ws &&
+             prefill_tc_workspace(p) > 0) {
     // stream-K persistent kernel: one CTA per SM, the work split computed on the device
     const int ctas = num_sms();
     PrefillSkArgs a;
     a.pairs = pairs;
-    a.arrive = prefill_arrive_counters(stream, ctas);
+    const size_t groups = (size_t)p.batch * p.num_kv_heads;
+    a.arrive = prefill_arrive_counters(stream, groups * ctas);
     a.ws_o = static_cast<float*>(ws);
-    a.ws_ml = a.ws_o + (size_t)2 * ctas * 2 * kBM * kD;
+    a.ws_ml = a.ws_o + groups * 2 * ctas * 2 * kBM * kD;
     const size_t smem = sizeof(PrefillSkSmem) + 1024;
-    VATTN_CUDA(cudaFuncSetAttribute(prefill_sk_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prefill_sk_kernel<T, 1><<<ctas, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
-                                                                      L.vmap_tail, L.pp, a);
+    // softmax flavour: 1 = every exponential on the MUFU, 2 = packed pairs + 3/8 of them on the FMA pipe
+    static const int mode = env_int("VATTN_PREFILL_MODE", 1);
+    auto launch_sk = [&](auto kernel) {
+      VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<ctas, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail, L.vmap_tail, L.pp, a);
+    };
+    if (mode == 2) launch_sk(prefill_sk_kernel<T, 2>);
+    else launch_sk(prefill_sk_kernel<T, 1>);
   } else if (p.seqlen_q > kBM && pair_items >= num_sms() && !env_int("VATTN_PREFILL_SINGLE", 0)) {
     // two row blocks per CTA, one CTA per (pair, head, batch entry): needs enough items to fill the SMs
     const size_t smem = sizeof(Prefill2KernelSmem) + 1024;
@@ -451,13 +445,15 @@ bool prefill_tc_supported(const vattn_fwd_params_t& p, std::string* why) {
 }
 
 size_t prefill_tc_workspace(const vattn_fwd_params_t& p) {
-  // stream-K: two partial slots per CTA, each [2 blocks][128 rows][128 + 2] fp32
+  // stream-K: two partial slots per (group, CTA), each [2 blocks][128 rows][128 + 2] fp32; beyond
+  // 512 MB (many kv heads x batch entries: plenty of items anyway) the grid kernel runs instead
   if (p.seqlen_q <= kBM) return 0;
-  return (size_t)2 * num_sms() * 2 * kBM * (kD + 2) * sizeof(float);
+  const size_t need = (size_t)p.batch * p.num_kv_heads * 2 * num_sms() * 2 * kBM * (kD + 2) * sizeof(float);
+  return need <= ((size_t)512 << 20) ? need : 0;
 }
 
 void launch_prefill_tc(const vattn_fwd_params_t& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  if (ws_bytes < prefill_tc_workspace(p)) ws = nullptr;  // (the POD fork passes its own carve-out)
+  if (prefill_tc_workspace(p) == 0 || ws_bytes < prefill_tc_workspace(p)) ws = nullptr;
   if (p.dtype == VATTN_DTYPE_BF16) launch_t<__nv_bfloat16>(p, ws, stream);
   else launch_t<__half>(p, ws, stream);
 }

@@ -695,6 +695,105 @@ __device__ __forceinline__ void regs_quarter_exp(const uint32_t (&r)[32], uint32
   }
 }
 
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2, one issue slot for two elements) + 3-input max ------
+// Measured on B200 (scripts/debug/pipe_throughput.cu): MUFU.EX2 16 / clk / SM in every format (f16x2 and
+// bf16x2 run at half the instruction rate, so they buy nothing), FFMA 128 / clk / SM, and the four
+// schedulers issue 128 thread-instructions / clk / SM in total.  A 128 x 128 score tile therefore costs
+// 1024 cycles of MUFU alone -- exactly the tensor-core time of its QK^T + PV -- so a softmax that sends
+// every exponential through the MUFU can at best tie with the MMAs.  MODE 2 takes ~3/8 of the
+// exponentials off the MUFU (degree-3 polynomial on the FMA pipe, the same constants as poly_exp2) and
+// halves the issue slots of everything else with packed pairs, FlashAttention-4's recipe.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// row max of one 32-column quarter, unmasked: 16 FMNMX3 in four independent chains
+__device__ __forceinline__ float regs_quarter_max3(const uint32_t (&r)[32]) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < 32; e += 8) {
+    m0 = max3(m0, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+    m1 = max3(m1, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+    m2 = max3(m2, __uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
+    m3 = max3(m3, __uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
+  }
+  return max3(fmaxf(m0, m1), m2, m3);
+}
+
+// 2^x for a packed pair on the FMA / ALU pipes (poly_exp2, two lanes at a time): clamp (2 FMNMX), split
+// x = n + f through the magic constant (3 packed adds), degree-3 Horner (3 FFMA2), n into the exponent
+// field (2 LEA)
+__device__ __forceinline__ uint64_t poly_exp2_x2(uint64_t x2) {
+  float xl, xh;
+  upk2(x2, xl, xh);
+  const uint64_t x = pk2(fmaxf(xl, -126.f), fmaxf(xh, -126.f));
+  const uint64_t magic = pk2(12582912.f, 12582912.f);
+  const uint64_t t = add2(x, magic);
+  const uint64_t f = sub2(x, sub2(t, magic));
+  uint64_t p = fma2(pk2(0.0551716086f, 0.0551716086f), f, pk2(0.242611118f, 0.242611118f));
+  p = fma2(p, f, pk2(0.693260997f, 0.693260997f));
+  p = fma2(p, f, pk2(0.999928074f, 0.999928074f));
+  float pl, ph, tl, th;
+  upk2(p, pl, ph);
+  upk2(t, tl, th);
+  return pk2(__int_as_float(__float_as_int(pl) + (__float_as_int(tl) << 23)),
+             __int_as_float(__float_as_int(ph) + (__float_as_int(th) << 23)));
+}
+
+// exponentials of one unmasked 32-column quarter, packed to 16 bit into out[0..15]; bit i of POLY_MASK
+// sends pair i of every 8 pairs through poly_exp2_x2 instead of the MUFU; row sums into two packed
+// accumulators
+template <typename T, uint32_t POLY_MASK>
+__device__ __forceinline__ void regs_quarter_exp_x2(const uint32_t (&r)[32], uint32_t* out, uint64_t scale2,
+                                                    uint64_t negm2, uint64_t (&l2)[2]) {
+#pragma unroll
+  for (int pr = 0; pr < 16; pr++) {
+    const uint64_t x = fma2(pk2u(r[2 * pr], r[2 * pr + 1]), scale2, negm2);
+    uint64_t p;
+    if ((POLY_MASK >> (pr & 7)) & 1u) {
+      p = poly_exp2_x2(x);
+    } else {
+      float xl, xh;
+      upk2(x, xl, xh);
+      p = pk2(fast_exp2(xl), fast_exp2(xh));
+    }
+    l2[pr & 1] = add2(l2[pr & 1], p);
+    float pl, ph;
+    upk2(p, pl, ph);
+    out[pr] = Elem<T>::from_f2(pl, ph);
+  }
+}
+
 // setmaxnreg (sm_90+): every warp of a warpgroup executes the same instruction
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
@@ -956,7 +1055,8 @@ struct PrefillSegment {
   // ---- parts > 1 only
   float* ws_o;         // [slot][2 blocks][128 rows][128] fp32, un-normalised
   float* ws_ml;        // [slot][2 blocks][128 rows][2]   (reference max in the log2 domain, row sum)
-  int my_slot;
+  int64_t slot_base;   // slot of part c = slot_base + 2 * (first_cta + c) + (that CTA's range starts inside the item)
+  int64_t my_slot;
   int first_cta;       // the parts are the CTAs first_cta .. first_cta + parts - 1
   int64_t item_start;  // flattened index of the item's tile 0 (to recompute the other parts' slots)
   StreamKPlan plan;
@@ -1132,6 +1232,9 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         if (warp_mask)
           mx = fmaxf(fmaxf(regs_quarter_max<true>(s0, key0, limit), regs_quarter_max<true>(s1, key0 + 32, limit)),
                      fmaxf(regs_quarter_max<true>(s2, key0 + 64, limit), regs_quarter_max<true>(s3, key0 + 96, limit)));
+        else if constexpr (MODE == 2)
+          mx = fmaxf(fmaxf(regs_quarter_max3(s0), regs_quarter_max3(s1)),
+                     fmaxf(regs_quarter_max3(s2), regs_quarter_max3(s3)));
         else
           mx = fmaxf(fmaxf(regs_quarter_max<false>(s0, 0, 0), regs_quarter_max<false>(s1, 0, 0)),
                      fmaxf(regs_quarter_max<false>(s2, 0, 0), regs_quarter_max<false>(s3, 0, 0)));
@@ -1167,9 +1270,16 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       if constexpr (REGS) {
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t packed[32];
+        // pairs 1, 4 and 6 of every 8 (3/8 of the exponentials) leave the MUFU in MODE 2
+        constexpr uint32_t kPolyMask = 0x52;
+        uint64_t l2[2] = {0ull, 0ull};
+        const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), negm2 = pk2(-mref_safe, -mref_safe);
         if (warp_mask) {
           regs_quarter_exp<T, true, 0>(s0, packed, p.scale_log2, mref_safe, key0, limit, ls);
           regs_quarter_exp<T, true, 0>(s1, packed + 16, p.scale_log2, mref_safe, key0 + 32, limit, ls);
+        } else if constexpr (MODE == 2) {
+          regs_quarter_exp_x2<T, kPolyMask>(s0, packed, scale2, negm2, l2);
+          regs_quarter_exp_x2<T, kPolyMask>(s1, packed + 16, scale2, negm2, l2);
         } else {
           regs_quarter_exp<T, false, 0>(s0, packed, p.scale_log2, mref_safe, 0, 0, ls);
           regs_quarter_exp<T, false, 0>(s1, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
@@ -1178,12 +1288,20 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         if (warp_mask) {
           regs_quarter_exp<T, true, 0>(s2, packed, p.scale_log2, mref_safe, key0 + 64, limit, ls);
           regs_quarter_exp<T, true, 0>(s3, packed + 16, p.scale_log2, mref_safe, key0 + 96, limit, ls);
+        } else if constexpr (MODE == 2) {
+          regs_quarter_exp_x2<T, kPolyMask>(s2, packed, scale2, negm2, l2);
+          regs_quarter_exp_x2<T, kPolyMask>(s3, packed + 16, scale2, negm2, l2);
         } else {
           regs_quarter_exp<T, false, 0>(s2, packed, p.scale_log2, mref_safe, 0, 0, ls);
           regs_quarter_exp<T, false, 0>(s3, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
         }
         tmem_st_x32(s_addr + 32, packed);  // keys 64..127
-        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        {
+          float a0, a1, b0, b1;
+          upk2(l2[0], a0, a1);
+          upk2(l2[1], b0, b1);
+          l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((a0 + a1) + (b0 + b1));
+        }
       } else {
         l += warp_mask ? tile_exp_store<T, true>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit)
                        : tile_exp_store<T, false>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit);
@@ -1267,14 +1385,14 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         float M = -INFINITY;
         for (int c = 0; c < seg.parts; c++) {
           const int cta = seg.first_cta + c;
-          const int64_t sl = 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+          const int64_t sl = seg.slot_base + 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
           M = fmaxf(M, __ldcg(seg.ws_ml + ((sl * 2 + t) * kBM + i) * 2));
         }
         const float Ms = (M == -INFINITY) ? 0.f : M;
         float L = 0.f;
         for (int c = 0; c < seg.parts; c++) {
           const int cta = seg.first_cta + c;
-          const int64_t sl = 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+          const int64_t sl = seg.slot_base + 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
           const int64_t row = (sl * 2 + t) * kBM + i;
           const float lc = __ldcg(seg.ws_ml + row * 2 + 1);
           if (lc > 0.f) L = fmaf(lc, fast_exp2(__ldcg(seg.ws_ml + row * 2) - Ms), L);
@@ -1287,7 +1405,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
           for (int e = 0; e < kD / 2; e++) acc[e] = 0.f;
           for (int c = 0; c < seg.parts; c++) {
             const int cta = seg.first_cta + c;
-            const int64_t sl = 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+            const int64_t sl = seg.slot_base + 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
             const int64_t row = (sl * 2 + t) * kBM + i;
             if (!(__ldcg(seg.ws_ml + row * 2 + 1) > 0.f)) continue;  // empty part: its O row was never written
             const float w = fast_exp2(__ldcg(seg.ws_ml + row * 2) - Ms);

@@ -20,7 +20,7 @@
 //   The tiles are independent, so the exchange of tile t overlaps the weight streaming of the
 //   other tiles; no separate collective launch, no partial round trip through HBM.
 //
-// Epochs live in device memory (epoch_state[0] = last completed call) so the launch is CUDA-graph
+// Epochs live in device memory (epoch_state[4 + tile] = last call this tile completed) so the launch is CUDA-graph
 // capturable; the receive slots and flags are double buffered on epoch parity.  Reuse is safe: a
 // rank writes parity e & 1 again in call e + 2, after its own call e + 1 finished, in which it
 // saw every peer's flag e + 1, which a peer only publishes after ITS call e (the last reader of
@@ -55,7 +55,7 @@ struct OprojParams {
   char* recv[kMaxWorld];       // rank r's receive area: [2][world][max_tokens][hidden]
   uint32_t* flags[kMaxWorld];  // rank r's flags: [2][n_tiles][kMaxWorld]
   char* out;                   // [tokens, hidden]
-  uint32_t* epoch_state;       // [0] last completed epoch, [1] CTAs done, [2] error (spin limit hit)
+  uint32_t* epoch_state;       // [2] error (spin limit hit); [4 + tile] last epoch completed by this tile's CTA
   int tokens, tokens_pad, hidden, k_steps, max_tokens, rank, world, n_tile, k_rot, stages;
 };
 
@@ -104,22 +104,41 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
   const int tile = blockIdx.x;
   const uint32_t tmem_cols = (uint32_t)p.n_tile;  // 32 / 64 / 128: a power of two >= 32
 
+  const uint32_t x_bytes = (uint32_t)p.tokens_pad * 128, stage_bytes = x_bytes + (uint32_t)p.n_tile * 128;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; s++) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
-    }
-    mbar_init(&sm.acc_full, 1);
-    fence_mbar_init();
-    sm.epoch = *reinterpret_cast<volatile uint32_t*>(p.epoch_state) + 1;
+    // every tile keeps its own epoch (all tiles of a launch hold the same value): no cross-CTA
+    // atomic and no "last CTA publishes" chain at the end of the kernel
+    sm.epoch = *reinterpret_cast<volatile uint32_t*>(p.epoch_state + 4 + tile) + 1;
   }
   if (warp == 5) {
     tmem_alloc(&sm.tmem_base, tmem_cols);
     tmem_relinquish();
   }
   if (warp == 4 && lane == 0) {
+    // ---- TMA producer: initialises the ring's barriers itself and starts streaming at once -- the
+    // TMEM allocation, the epoch load and the CTA barrier below overlap the first loads' latency
     prefetch_tensormap(&w_map);
     prefetch_tensormap(&x_map);
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    mbar_init(&sm.acc_full, 1);
+    fence_mbar_init();
+    // every CTA needs the same [tokens x 64] activation atom at step k: start each tile at a
+    // different k so the 128 CTAs do not hammer one L2 line set at the same moment
+    const int k_first = (int)(((long long)tile * p.k_rot) % p.k_steps);
+    const int first = p.stages < p.k_steps ? p.stages : p.k_steps;
+    auto issue = [&](int k) {
+      const int s = k % p.stages;
+      int kk = k + k_first;
+      if (kk >= p.k_steps) kk -= p.k_steps;
+      mbar_expect_tx(&sm.full[s], stage_bytes);
+      uint8_t* st = sm.ring + (size_t)s * stage_bytes;
+      tma_load_2d(st, &x_map, &sm.full[s], kk * kKStep, 0);
+      tma_load_2d(st + x_bytes, &w_map, &sm.full[s], kk * kKStep, tile * p.n_tile);
+    };
+    for (int k = 0; k < first; k++) issue(k);  // the whole ring before anybody else is ready
   }
   tc_fence_before();
   __syncthreads();
@@ -127,19 +146,16 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
   const uint32_t tmem = sm.tmem_base;
   const uint32_t epoch = sm.epoch;
   const int parity = epoch & 1;
-  const uint32_t x_bytes = (uint32_t)p.tokens_pad * 128, stage_bytes = x_bytes + (uint32_t)p.n_tile * 128;
 
   if (warp == 4) {
-    // ---- TMA producer
+    // ---- TMA producer, steady state (k >= stages): refill a slot as soon as the MMA released it
     if (lane == 0) {
-      // every CTA needs the same [tokens x 64] activation atom at step k: start each tile at a
-      // different k so the 128 CTAs do not hammer one L2 line set at the same moment
       const int k_first = (int)(((long long)tile * p.k_rot) % p.k_steps);
-      for (int k = 0; k < p.k_steps; k++) {
+      for (int k = p.stages; k < p.k_steps; k++) {
         const int s = k % p.stages;
         int kk = k + k_first;
         if (kk >= p.k_steps) kk -= p.k_steps;
-        if (k >= p.stages) mbar_wait(&sm.empty[s], ((k / p.stages) - 1) & 1);
+        mbar_wait(&sm.empty[s], ((k / p.stages) - 1) & 1);
         mbar_expect_tx(&sm.full[s], stage_bytes);
         uint8_t* st = sm.ring + (size_t)s * stage_bytes;
         tma_load_2d(st, &x_map, &sm.full[s], kk * kKStep, 0);
@@ -198,7 +214,8 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
       }
     }
     tc_fence_before();
-    __threadfence_system();
+    // st.release.sys below is cumulative: after this CTA barrier it orders the pushes of all 128
+    // threads before the flag, so no per-thread system fence is needed
     named_bar_sync(1, 128);
     const size_t flag_row = ((size_t)parity * gridDim.x + tile) * kMaxWorld;
     if (t < p.world) {
@@ -242,15 +259,7 @@ oproj_allreduce_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_c
   }
   __syncthreads();
   if (warp == 5) tmem_dealloc(tmem, tmem_cols);
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t done = atomicAdd(p.epoch_state + 1, 1u);
-    if (done == gridDim.x - 1) {  // last CTA of this call: publish the epoch for the next launch
-      p.epoch_state[1] = 0;
-      __threadfence();
-      *reinterpret_cast<volatile uint32_t*>(p.epoch_state) = epoch;
-    }
-  }
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(p.epoch_state + 4 + tile) = epoch;  // next launch: +1
 }
 
 }  // namespace

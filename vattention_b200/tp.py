@@ -211,7 +211,8 @@ class FusedOProjAllReduce:
             bases = [int(p) for p in self.handle.buffer_ptrs]
         self._recv = (C.c_uint64 * self.world)(*bases)
         self._flags = (C.c_uint64 * self.world)(*[b + self.recv_bytes for b in bases])
-        self.epoch_state = torch.zeros(4, dtype=torch.int32, device=self.device)
+        # [2] error flag, [4 + tile] per-tile epoch (tiles of 32 hidden columns at most)
+        self.epoch_state = torch.zeros(4 + self.hidden // 32, dtype=torch.int32, device=self.device)
         self.out = torch.empty(max_tokens, self.hidden, dtype=self.dtype, device=self.device)
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
