@@ -166,10 +166,10 @@ def pod(args):
         out["pod_call_vs_serial"] = round(t_s / t_f, 4)
         out["persistent_kernel_ms"] = round(t_k, 3)
         out["persistent_kernel_vs_serial"] = round(t_s / t_k, 4)
-        if args.lean:       # co-resident configurations (fused_params 64), opt-in until measured
-            t_l = timed(lambda: run_fused(64), 1, args.iters)
-            out["lean_ms"] = round(t_l, 3)
-            out["lean_vs_serial"] = round(t_s / t_l, 4)
+        # the dual-role kernel (fused_params 64): a prefill and a decode pipeline in every CTA
+        t_l = timed(lambda: run_fused(64), 1, args.iters)
+        out["dual_role_kernel_ms"] = round(t_l, 3)
+        out["dual_role_kernel_vs_serial"] = round(t_s / t_l, 4)
     print(json.dumps(out))
 
 
@@ -296,7 +296,6 @@ if __name__ == "__main__":
     ap.add_argument("--decodes", type=int, default=56)
     ap.add_argument("--decode-len", type=int, default=4096)
     ap.add_argument("--ragged", action="store_true")
-    ap.add_argument("--lean", action="store_true", help="pod: also time the co-resident (fused_params 64) strategy")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--hq", type=int, default=32)
     ap.add_argument("--hkv", type=int, default=8)

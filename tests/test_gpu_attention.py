@@ -321,14 +321,13 @@ def test_against_flash_attn_library_if_present():
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("fused_params", [15, 9, pytest.param(64, marks=pytest.mark.skipif(
-    __import__("os").environ.get("VATTN_TEST_POD_LEAN") != "1", reason="opt-in: VATTN_TEST_POD_LEAN=1"))])
+@pytest.mark.parametrize("fused_params", [15, 9, 64])
 def test_pod_fused_many_items_matches_oracle(dtype, fused_params):
     """fused_params 9 (an explicit configuration) = the persistent fused kernel: enough prefill row
     blocks and decode chunks that every CTA runs several work items of both kinds (barrier
     re-initialisation, TMEM reuse, ticket order).  15 (auto) = the two specialised kernels
-    co-scheduled on two streams with a fork/join inside the call.  64 = the same with the kernels'
-    co-resident ("lean") configurations; unmeasured so far, hence opt-in."""
+    co-scheduled on two streams with a fork/join inside the call.  64 = the dual-role kernel: every CTA
+    carries a prefill pipeline and a decode pipeline side by side (pod_dual_kernel)."""
     g = torch.Generator().manual_seed(77)
     Hq, Hkv, D = 8, 2, 128
     Bp, Sq, Sk = 2, 700, 1500

@@ -40,7 +40,6 @@ using namespace tcwork;
 constexpr int kStages = 3;               // 3 x 32 KB ring per CTA, 2 CTAs per SM
 constexpr int kMaxTilesPerChunk = 16;
 
-constexpr int kLeanStages = 2;            // co-resident POD arrangement: 2 x 32 KB ring beside a prefill CTA
 
 template <int STAGES>
 struct __align__(1024) DecodeKernelSmemT {
@@ -233,7 +232,7 @@ bool decode_uses_stream_k(const vattn_fwd_params_t& p) {
     const char* e = std::getenv("VATTN_DECODE_SCHED");
     return e && std::string(e) == "streamk";
   }();
-  return sk && p.num_splits <= 0 && !t_pod_lean;
+  return sk && p.num_splits <= 0;
 }
 int stream_k_ctas() { return num_sms() * 2; }
 size_t stream_k_workspace(const vattn_fwd_params_t& p) {
@@ -254,7 +253,6 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
   const int group = p.num_heads / p.num_kv_heads;
   DecodeTcLaunch L;
   build_decode_tc(p, ws, stream, &L, true);
-  const bool lean = t_pod_lean;
   if (L.stream_k) {
     const size_t smem = sizeof(DecodeSkSmemT<kStages>) + 1024;
     auto launch_sk = [&](auto kernel) {
@@ -270,7 +268,7 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
     VATTN_CUDA(cudaGetLastError());
     return;
   }
-  const size_t smem = (lean ? sizeof(DecodeKernelSmemT<kLeanStages>) : sizeof(DecodeKernelSmem)) + 1024;
+  const size_t smem = sizeof(DecodeKernelSmem) + 1024;
   dim3 grid(L.dp.num_chunks, p.num_kv_heads, p.batch);
   auto launch = [&](auto kernel) {
     // all GP instantiations share one function-pointer type, so a static flag here would be
@@ -280,11 +278,7 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
     kernel<<<grid, kThreads, smem, stream>>>(L.kmap, L.vmap, L.kmap_tail, L.vmap_tail, L.dp);
     timing_end(tslot, stream);
   };
-  if (lean) {
-    if (group <= 4) launch(decode_tc_kernel<T, 4, kLeanStages>);
-    else if (group <= 8) launch(decode_tc_kernel<T, 8, kLeanStages>);
-    else launch(decode_tc_kernel<T, 16, kLeanStages>);
-  } else if (group <= 4) launch(decode_tc_kernel<T, 4>);
+  if (group <= 4) launch(decode_tc_kernel<T, 4>);
   else if (group <= 8) launch(decode_tc_kernel<T, 8>);
   else launch(decode_tc_kernel<T, 16>);
   count_launch();

@@ -76,50 +76,6 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constan
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-// The co-resident POD arrangement (prefill_work<T, 3, true>): Q 32 KB + 3 x 32 KB ring, TMEM S x2 (256
-// columns, P in place) + O (128 columns, second allocation) -- leaves 98 KB of shared memory, 128 TMEM
-// columns and (at <= 184 registers x 256 threads) a quarter of the register file for a decode CTA.
-constexpr int kLeanStages = 3;
-struct __align__(1024) PrefillLeanKernelSmem {
-  PrefillSmemT<kLeanStages> data;
-  TcBarriers bar;
-  uint32_t tmem_base, tmem_base_o;
-};
-
-// 160 registers x 256 threads + a decode CTA's 96 x 256 = the whole register file
-template <typename T>
-__global__ void __maxnreg__(160)
-prefill_lean_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
-                       const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap kmap_tail,
-                       const __grid_constant__ CUtensorMap vmap_tail, const PrefillParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  PrefillLeanKernelSmem& sm =
-      *reinterpret_cast<PrefillLeanKernelSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
-  if (warp == 0 && (threadIdx.x & 31) == 0) {
-    prefetch_tensormap(&qmap);
-    prefetch_tensormap(&kmap);
-    prefetch_tensormap(&vmap);
-  }
-  if (warp == 2) {
-    tmem_alloc(&sm.tmem_base, 256);
-    tmem_alloc(&sm.tmem_base_o, 128);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sm.tmem_base, tmem_o = sm.tmem_base_o;
-  const int mt = p.num_m_tiles - 1 - blockIdx.x;
-  prefill_work<T, kLeanStages, true>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, mt,
-                                     blockIdx.y, blockIdx.z, false, tmem_o);
-  __syncthreads();
-  if (warp == 2) {
-    tmem_dealloc(tmem, 256);
-    tmem_dealloc(tmem_o, 128);
-  }
-}
-
 struct __align__(1024) Prefill2KernelSmem {
   Prefill2Smem data;
   TcBarriers bar;
@@ -346,13 +302,7 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
     const char* e = std::getenv("VATTN_PREFILL_SCHED");
     return e && std::string(e) == "grid";
   }();
-  if (t_pod_lean) {
-    const size_t smem = sizeof(PrefillLeanKernelSmem) + 1024;
-    VATTN_CUDA(cudaFuncSetAttribute(prefill_lean_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(L.pp.num_m_tiles, p.num_heads, p.batch);
-    prefill_lean_tc_kernel<T><<<grid, kThreads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail, L.vmap_tail,
-                                                                L.pp);
-  } else if (p.seqlen_q > kBM && !grid_forced && (long long)p.batch * pairs <= kSkMaxEntries && ws &&
+  if (p.seqlen_q > kBM && !grid_forced && (long long)p.batch * pairs <= kSkMaxEntries && ws &&
              prefill_tc_workspace(p) > 0) {
     // stream-K persistent kernel: one CTA per SM, the work split computed on the device
     const int ctas = num_sms();

@@ -26,11 +26,6 @@ struct PrefillTcLaunch {
 };
 void build_prefill_tc(const vattn_fwd_params_t& p, PrefillTcLaunch* out);
 
-// Set (per host thread) by vattn_pod_fwd around the two launches of its "lean" strategy: the prefill
-// launcher then uses the 128 KB / 384-TMEM-column kernel and the decode launcher the 2-stage ring, so
-// that one CTA of each fits on an SM at the same time.
-extern thread_local bool t_pod_lean;
-
 bool decode_tc_supported(const vattn_fwd_params_t& p, std::string* why);
 bool prefill_tc_supported(const vattn_fwd_params_t& p, std::string* why);
 size_t decode_tc_workspace(const vattn_fwd_params_t& p);

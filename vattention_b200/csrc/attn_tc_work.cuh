@@ -40,6 +40,30 @@ __device__ __forceinline__ void mbar_reinit(uint64_t* bar, uint32_t count, bool 
 }
 
 
+// Which warps of the CTA run one pipeline, and the barrier they synchronise on.  The stand-alone
+// kernels and the persistent POD kernel give a whole CTA to one work item at a time (Side{}: warp 0
+// TMA producer, warp 1 MMA issuer, warps 4-7 softmax, __syncthreads).  The dual-role POD kernel runs a
+// prefill pipeline and a decode pipeline side by side in ONE CTA: each gets its own warps, its own
+// named barrier, its own shared memory and TMEM columns, and pulls its own work items.
+struct Side {
+  int tma_warp = 0, mma_warp = 1, sm_warp0 = 4;  // softmax warps sm_warp0 .. sm_warp0 + 3
+  int bar_id = 0;                                // 0: __syncthreads(); else named barrier of `nthreads`
+  int nthreads = 0;                              // threads of the side (0: blockDim.x)
+  // linear index of the calling thread inside the side (whole-CTA side: threadIdx.x)
+  __device__ __forceinline__ int tid() const {
+    if (bar_id == 0) return threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == tma_warp) return lane;
+    if (warp == mma_warp) return 32 + lane;
+    return 64 + (warp - sm_warp0) * 32 + lane;
+  }
+  __device__ __forceinline__ int size() const { return bar_id == 0 ? (int)blockDim.x : nthreads; }
+  __device__ __forceinline__ void sync() const {
+    if (bar_id == 0) __syncthreads();
+    else named_bar_sync(bar_id, nthreads);
+  }
+};
+
 // Stage rows [row0, row0 + 128) of one (head, slot) of a K or V cache into a ring slot.  Rows at or
 // beyond `safe_rows` (the sequence length rounded up to `tail_rows`, itself a divisor of
 // tokens_per_page) may lie in unmapped virtual memory and are never requested: a tile that is
@@ -134,7 +158,7 @@ template <typename T, int GP, int STAGES>
 __device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap, const CUtensorMap* kmap_tail,
                                const CUtensorMap* vmap_tail, const DecodeTcParams& p,
                                DecodeSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem, const DecodeSegment& seg,
-                               bool barriers_live) {
+                               bool barriers_live, const Side sd = Side{}) {
   static_assert(STAGES <= kMaxStages, "ring deeper than the barrier block");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = seg.b, hkv = seg.hkv;
@@ -147,8 +171,8 @@ __device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap,
   const int h0 = hkv * G;
 
   if (seg.publish_empty) {  // CTA-uniform: this chunk lies past the sequence
-    if (threadIdx.x < G) {
-      const int64_t base = seg.part_idx + threadIdx.x * seg.part_stride_g;
+    if (sd.tid() < G) {
+      const int64_t base = seg.part_idx + sd.tid() * seg.part_stride_g;
       p.ws_ml[base * 2] = -INFINITY;
       p.ws_ml[base * 2 + 1] = 0.f;
     }
@@ -156,15 +180,15 @@ __device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap,
   }
   if (n == 0 && !owns_new) {
     // zero-length sequence, nothing appended: output zeros (softmax.h:76-78 convention)
-    for (int i = threadIdx.x; i < G * kHeadDim; i += blockDim.x)
+    for (int i = sd.tid(); i < G * kHeadDim; i += sd.size())
       reinterpret_cast<T*>(p.out + b * p.o_b + (int64_t)(h0 + i / kHeadDim) * p.o_h)[i % kHeadDim] =
           Elem<T>::from_f(0.f);
-    if (p.lse && threadIdx.x < G) p.lse[(int64_t)b * p.num_heads + h0 + threadIdx.x] = INFINITY;
+    if (p.lse && sd.tid() < G) p.lse[(int64_t)b * p.num_heads + h0 + sd.tid()] = INFINITY;
     return;
   }
 
   // ---------------------------------------------------------------- setup ----
-  if (threadIdx.x == 0) {
+  if (sd.tid() == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_reinit(&bar.full[s], 1, barriers_live);
       mbar_reinit(&bar.empty[s], 1, barriers_live);
@@ -179,18 +203,18 @@ __device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap,
   {
     // zero Q and P^T (rows >= G must stay zero), then stage this group's query heads
     uint32_t* z = reinterpret_cast<uint32_t*>(sm.q);
-    for (int i = threadIdx.x; i < (int)(sizeof(sm.q) + sizeof(sm.p)) / 4; i += blockDim.x) z[i] = 0;
+    for (int i = sd.tid(); i < (int)(sizeof(sm.q) + sizeof(sm.p)) / 4; i += sd.size()) z[i] = 0;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < G * (kHeadDim / 8); i += blockDim.x) {
+  sd.sync();
+  for (int i = sd.tid(); i < G * (kHeadDim / 8); i += sd.size()) {
     const int g = i / (kHeadDim / 8), c8 = i % (kHeadDim / 8);  // 16-byte chunk c8 of head g
     const uint4 v = *reinterpret_cast<const uint4*>(p.q + b * p.q_b + (int64_t)(h0 + g) * p.q_h + c8 * 16);
     *reinterpret_cast<uint4*>(sm.q[c8 >> 3] + sw128_off(g, (c8 & 7) * 8)) = v;
   }
   fence_proxy_async_smem();
-  __syncthreads();
+  sd.sync();
 
-  if (warp == 0) {
+  if (warp == sd.tma_warp) {
     // =========================================================== TMA producer ====
     if (lane == 0) {
       int pos = 0;
@@ -208,7 +232,7 @@ __device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap,
         if (j + 2 < n) load(kmap, kmap_tail, j + 2);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == sd.mma_warp) {
     // ============================================================ MMA issuer ====
     if (lane == 0 && n > 0) {
       int pos = 0;
@@ -254,10 +278,10 @@ __device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap,
         if (j + 2 < n) issue_qk(j + 2);
       }
     }
-  } else if (warp >= 4 && warp < 8) {  // (a 384-thread CTA leaves warps 8-11 idle here)
+  } else if (warp >= sd.sm_warp0 && warp < sd.sm_warp0 + 4) {  // (other warps of the side idle here)
     // ================================================= softmax / accumulate ====
-    const int t = threadIdx.x - 128;  // key index inside a tile for S^T, head dim for O^T
-    const int sw = warp - 4;          // TMEM lane quadrant of this warp
+    const int t = threadIdx.x - sd.sm_warp0 * 32;  // key index inside a tile for S^T, head dim for O^T
+    const int sw = warp - sd.sm_warp0;             // TMEM lane quadrant of this warp (sm_warp0 % 4 == 0)
     const uint32_t lane_base = (uint32_t)(sw * 32) << 16;
     float m_run[GP], l_thr[GP], acc[GP], alpha_prev[GP];
 #pragma unroll
@@ -479,7 +503,7 @@ __device__ void decode_segment(const CUtensorMap* kmap, const CUtensorMap* vmap,
     }
   }
   tc_fence_before();
-  __syncthreads();
+  sd.sync();
 }
 
 // Classic grid: one segment per (chunk of tiles_per_chunk tiles, kv head, batch entry); partial layout
@@ -488,7 +512,7 @@ template <typename T, int GP, int STAGES>
 __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, const CUtensorMap* kmap_tail,
                             const CUtensorMap* vmap_tail, const DecodeTcParams& p,
                             DecodeSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem, int chunk, int hkv,
-                            int b, bool barriers_live) {
+                            int b, bool barriers_live, const Side sd = Side{}) {
   const bool fused_new = p.k_new != nullptr;
   DecodeSegment seg;
   seg.b = b, seg.hkv = hkv;
@@ -512,7 +536,7 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
   // an empty sequence with nothing appended: with the separate combine kernel its slot 0 must be a
   // well-formed empty partial too (the combine then writes the zeros / +inf lse)
   if (seg.n == 0 && !seg.owns_new && !p.arrive && p.num_chunks > 1) seg.publish_empty = true;
-  decode_segment<T, GP, STAGES>(kmap, vmap, kmap_tail, vmap_tail, p, sm, bar, tmem, seg, barriers_live);
+  decode_segment<T, GP, STAGES>(kmap, vmap, kmap_tail, vmap_tail, p, sm, bar, tmem, seg, barriers_live, sd);
 }
 
 // ---- stream-K schedule over the flattened (batch, kv head, key tile) space ---------------------
@@ -812,7 +836,8 @@ template <typename T, int STAGES = kPrefillStages, bool LEAN = false>
 __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
                              const CUtensorMap* kmap_tail, const CUtensorMap* vmap_tail,
                              const PrefillParams& p, PrefillSmemT<STAGES>& sm, TcBarriers& bar, uint32_t tmem,
-                             int mt, int h, int b, bool barriers_live, uint32_t tmem_o = 0) {
+                             int mt, int h, int b, bool barriers_live, uint32_t tmem_o = 0,
+                             const Side sd = Side{}) {
   constexpr int kStages = STAGES;
   constexpr int kBM = kTile, kBN = kTile, kD = kHeadDim;
   const int hkv = h / p.group;
@@ -828,7 +853,7 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
   if (kv_end < 0) kv_end = 0;
   const int n = (kv_end + kBN - 1) / kBN;
 
-  if (threadIdx.x == 0) {
+  if (sd.tid() == 0) {
     mbar_reinit(&bar.q_full, 1, barriers_live);
     for (int s = 0; s < kStages; s++) {
       mbar_reinit(&bar.full[s], 1, barriers_live);
@@ -841,9 +866,9 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
     }
     fence_mbar_init();
   }
-  __syncthreads();
+  sd.sync();
 
-  if (warp == 0) {
+  if (warp == sd.tma_warp) {
     // =========================================================== TMA producer ====
     if (lane == 0 && n > 0) {
       mbar_expect_tx(&bar.q_full, kBM * kD * 2);
@@ -863,7 +888,7 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
         if (j + 2 < n) load(kmap, kmap_tail, j + 2);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == sd.mma_warp) {
     // ============================================================ MMA issuer ====
     if (lane == 0 && n > 0) {
       int pos = 0;
@@ -909,10 +934,10 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
         if (j + 2 < n) issue_qk(j + 2);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= sd.sm_warp0 && warp < sd.sm_warp0 + 4) {
     // ==================================================== softmax / epilogue ====
-    const int i = threadIdx.x - 128;  // query row inside the block == TMEM lane
-    const int sw = warp - 4;
+    const int i = threadIdx.x - sd.sm_warp0 * 32;  // query row inside the block == TMEM lane
+    const int sw = warp - sd.sm_warp0;
     const uint32_t lane_base = (uint32_t)(sw * 32) << 16;
     const int qi = m0 + i;
     // last visible key (inclusive) for this row; < 0 means the row sees nothing
@@ -1020,7 +1045,7 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
           l > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : INFINITY;
   }
   tc_fence_before();
-  __syncthreads();
+  sd.sync();
 }
 
 

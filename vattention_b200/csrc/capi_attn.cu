@@ -42,6 +42,7 @@ size_t rope_workspace_bytes(const vattn_fwd_params_t&);
 vattn_fwd_params_t rope_rotated_view(const vattn_fwd_params_t&, const void*, const void*);
 vattn_fwd_params_t launch_rope(const vattn_fwd_params_t&, cudaStream_t);
 void launch_pod_tc(const vattn_fwd_params_t&, const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
+void launch_pod_dual(const vattn_fwd_params_t&, const vattn_fwd_params_t&, void* ws, size_t ws_bytes, cudaStream_t);
 
 // ---- per-launch kernel timing -------------------------------------------------------
 namespace {
@@ -53,7 +54,6 @@ struct TimingState {
 } g_timing;
 }  // namespace
 
-thread_local bool t_pod_lean = false;  // attn_tc_host.h
 
 // ---- arrival counters (attn_common.cuh) ---------------------------------------------------------
 namespace {
@@ -375,30 +375,25 @@ PodSide& pod_side_for(cudaStream_t main) {
   }
   return s;
 }
-struct LeanScope {  // marks the launches of one vattn_pod_fwd call as "lean" (attn_tc_host.h)
-  explicit LeanScope(bool on) { t_pod_lean = on; }
-  ~LeanScope() { t_pod_lean = false; }
-};
-enum class PodStrategy { Streams, Kernel, Serial, Lean };
+enum class PodStrategy { Streams, Kernel, Serial, Dual };
 PodStrategy pod_strategy(int32_t fused_params) {
   // the reference: 15 = "pick the most suitable" (fused_api.cpp:24-53), anything else names one
-  // tile configuration of its fused kernel.  Here: 15 -> the fastest measured arrangement, which is
-  // the two specialised kernels co-scheduled on two streams (SM-level overlap by the block
-  // scheduler; bench_extra.py pod: 1.13x over serial on a balanced hybrid batch where the
-  // persistent single kernel is 0.89x); an explicit configuration -> the persistent fused kernel.
-  // VATTN_POD_STRATEGY=streams|kernel|serial|lean overrides.  "lean" = streams with the kernels'
-  // co-resident configurations (prefill: 128 KB, 384 TMEM columns; decode: 2-stage ring), prefill
-  // launched first so that every SM holds one prefill CTA and one decode CTA at the same time: the
-  // arrangement that should turn the overlap from SM-level partitioning into true sharing of an SM's
-  // tensor pipe and HBM queue.  Written, not yet measured: opt-in.
+  // tile configuration of its fused kernel.  Here:
+  //   Dual    ONE launch, every CTA carries a prefill pipeline and a decode pipeline side by side
+  //           (attn_pod_tc.cu: pod_dual_kernel) -- true sharing of an SM's tensor pipe and memory queue;
+  //   Streams the two specialised kernels co-scheduled on two streams (fork / join inside the call);
+  //   Kernel  the persistent one-item-at-a-time kernel (pod_tc_kernel);
+  //   Serial  the two kernels back to back.
+  // VATTN_POD_STRATEGY=dual|streams|kernel|serial overrides; otherwise 15 -> the default below, an
+  // explicit configuration -> Kernel.
   if (const char* e = std::getenv("VATTN_POD_STRATEGY")) {
     const std::string v(e);
     if (v == "kernel") return PodStrategy::Kernel;
     if (v == "serial") return PodStrategy::Serial;
     if (v == "streams") return PodStrategy::Streams;
-    if (v == "lean") return PodStrategy::Lean;
+    if (v == "dual") return PodStrategy::Dual;
   }
-  if (fused_params == 64) return PodStrategy::Lean;  // our own value: none of the reference's configurations
+  if (fused_params == 64) return PodStrategy::Dual;  // our own value: none of the reference's configurations
   return fused_params == 15 ? PodStrategy::Streams : PodStrategy::Kernel;
 }
 }  // namespace
@@ -416,6 +411,10 @@ int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* d
       launch_pod_tc(*prefill, *decode, workspace, workspace_bytes, main);
       return VATTN_OK;
     }
+    if (strat == PodStrategy::Dual && pod_fused_path(prefill, decode)) {
+      launch_pod_dual(*prefill, *decode, workspace, workspace_bytes, main);
+      return VATTN_OK;
+    }
     // the two specialised kernels: co-scheduled on two streams, or back to back (one side missing,
     // serial requested)
     size_t a = prefill ? vattn_fwd_kvcache_workspace(prefill) : 0;
@@ -423,23 +422,6 @@ int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* d
     const bool both = prefill && decode && prefill->batch > 0 && decode->batch > 0;
     const bool fork = both && strat != PodStrategy::Serial;
     PodSide* side = fork ? &pod_side_for(main) : nullptr;
-    std::string why;
-    if (fork && strat == PodStrategy::Lean && prefill->seqlen_q > 1 && decode->seqlen_q == 1 &&
-        prefill->impl != VATTN_IMPL_SIMT && decode->impl != VATTN_IMPL_SIMT &&
-        prefill_tc_supported(*prefill, &why) && decode_tc_supported(*decode, &why)) {
-      LeanScope lean(true);
-      vattn_fwd_params_t p = *prefill, d = *decode;
-      p.workspace = workspace, p.workspace_bytes = a;
-      d.workspace = workspace ? static_cast<char*>(workspace) + a : nullptr;
-      d.workspace_bytes = workspace_bytes > a ? workspace_bytes - a : 0;
-      VATTN_CUDA(cudaEventRecord(side->fork, main));
-      VATTN_CUDA(cudaStreamWaitEvent(side->side, side->fork, 0));
-      run_fwd(p, main);        // prefill first: one CTA per SM, leaving room for one decode CTA beside it
-      run_fwd(d, side->side);
-      VATTN_CUDA(cudaEventRecord(side->join, side->side));
-      VATTN_CUDA(cudaStreamWaitEvent(main, side->join, 0));
-      return VATTN_OK;
-    }
     if (decode) {
       vattn_fwd_params_t d = *decode;
       d.workspace = workspace ? static_cast<char*>(workspace) + a : nullptr;
