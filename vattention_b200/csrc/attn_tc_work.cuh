@@ -1239,8 +1239,24 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
     float m_ref = -INFINITY, l = 0.f;
     const uint32_t s_addr = tmem + lane_base + kCol2S + t * kBN;
     const uint32_t o_addr = tmem + lane_base + kCol2O + t * kD;
+    // Ping-pong token (FlashAttention-3's scheduler barriers): the exponential pass of one warpgroup
+    // never overlaps the other's.  Left alone the two blocks lock IN phase -- the MMA thread issues
+    // PV0 QK0 PV1 QK1 back to back whenever both P tiles are ready, both S tiles come back together,
+    // both warpgroups then share the MUFU (2048 cycles for the pair) while the tensor pipe idles, and
+    // the period is ~4100 cycles for 2048 of MMA: ncu measured tensor 47 %, XU 52 %, softmax warps
+    // stalled on S 31 % of their samples.  With the token warpgroup 1 starts its exponentials when
+    // warpgroup 0 finishes, so block 0's PV / QK^T run under block 1's exponentials and vice versa.
+    // Named barriers 6 (token for block 0) and 7 (block 1), 128 waiters + 128 arrivers each; block 1
+    // hands out the first token and keeps its last one; a block with fewer tiles keeps passing it on.
+    const uint32_t tok_mine = 6 + t, tok_other = 6 + (t ^ 1);
+    if (t == 1 && n > 0) named_bar_arrive(6, 256);
 
-    for (int j = 0; j < my_n; j++) {
+    for (int j = 0; j < n; j++) {
+      if (j >= my_n) {  // nothing left for this block: keep the token moving
+        named_bar_sync(tok_mine, 256);
+        if (t == 0 || j < n - 1) named_bar_arrive(tok_other, 256);
+        continue;
+      }
       mbar_wait(&bar.s_full[t], j & 1);
       tc_fence_after();
       const int key0 = (j0 + j) * kBN;
@@ -1291,6 +1307,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       }
       l *= alpha;
       const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
+      named_bar_sync(tok_mine, 256);  // the MUFU is ours until the exponentials are done
       // P_t(j) overwrites the already consumed low half of S_t (in place)
       if constexpr (REGS) {
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1331,6 +1348,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         l += warp_mask ? tile_exp_store<T, true>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit)
                        : tile_exp_store<T, false>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit);
       }
+      if (t == 0 || j < n - 1) named_bar_arrive(tok_other, 256);
       tmem_wait_st();
       if ((j0 + j + 1) * kBN > lk) {
         const int pv = 2 * j + 1;

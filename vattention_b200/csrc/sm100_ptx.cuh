@@ -52,6 +52,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// arrive without waiting: completes the barrier for the `nthreads - arrivals` threads that bar.sync on it
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ----------------------------------------------------------------------- TMA ----
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
