@@ -207,18 +207,32 @@ int tiles_per_chunk_for(const vattn_fwd_params_t& p) {
     return (nt + p.num_splits - 1) / p.num_splits;
   }
   const int64_t nt = (p.seqlen_k + kTile - 1) / kTile;
-  const int64_t total = nt * p.batch * p.num_kv_heads;
-  // one chunk per resident CTA slot (SMs x 2) when the problem is small, chunks of at most 16
-  // tiles (2048 keys) when it is large.  Measured (profiles/r1_decode_chunk_sweep.jsonl): the
-  // per-CTA prologue (TMEM, barriers, Q, ring fill) and the split combine cost more than an uneven
-  // last wave -- B16 x Hkv1 x 32K runs 72.7 us with 16-tile chunks, 91 us with 4, 180 us with 1
+  const int64_t seqs = (int64_t)p.batch * p.num_kv_heads;
+  const int64_t total = nt * seqs;
+  // Large problems: chunks of 16 tiles (2048 keys), many waves, the block scheduler balances them.
+  // Small problems (everything fits one wave of 2 CTAs per SM with <= 16 tiles each... or fewer tiles
+  // than that): ONE wave -- as many chunks per sequence as resident CTA slots allow, never more CTAs
+  // than slots.  The per-CTA prologue (TMEM, barriers, Q, ring fill) and epilogue cost ~8 us, so a
+  // partial second wave is expensive: ncu on B16 x Hkv1 x 32K showed 320 CTAs of 13 tiles on 296 slots
+  // = 1.08 waves, 68 us, DRAM 49 % busy (profiles/r2_decode_small_grid_ncu.md); measured sweep of
+  // round 1: 72.7 us with 16-tile chunks, 91 us with 4, 180 us with 1.
   static const int forced = env_int("VATTN_DECODE_TPC", 0);
   const int64_t slots = (int64_t)num_sms() * 2;
-  int64_t tpc = total / slots;
-  if (tpc < 1) tpc = 1;
-  if (tpc > kMaxTilesPerChunk) tpc = kMaxTilesPerChunk;
+  int64_t tpc = kMaxTilesPerChunk;
+  if (total <= slots * kMaxTilesPerChunk) {
+    const int64_t cps = seqs >= slots ? 1 : slots / seqs;  // chunks per sequence: seqs * cps <= slots
+    tpc = (nt + cps - 1) / cps;
+    if (tpc < 1) tpc = 1;
+  }
   if (forced > 0) tpc = forced;  // experiments may exceed the cap (the kernel loops over any count)
   return (int)tpc;
+}
+
+// one wave of CTAs and few chunks per sequence: the last chunk of a sequence to finish reduces the
+// partials inside the sweep (no combine launch); VATTN_DECODE_COMBINE_INKERNEL=0|1 overrides
+bool decode_small_problem(const vattn_fwd_params_t& p) {
+  const int64_t nt = (p.seqlen_k + kTile - 1) / kTile;
+  return nt * p.batch * p.num_kv_heads <= (int64_t)num_sms() * 2 * kMaxTilesPerChunk;
 }
 
 // Schedules.  Default: the (chunk, kv head, batch) grid + combine kernel -- the hardware block scheduler
@@ -328,7 +342,8 @@ void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream,
   // split partials are reduced by combine_kernel; VATTN_DECODE_COMBINE_INKERNEL=1 lets the last chunk of
   // a sequence to arrive do it inside the sweep instead (one launch less, but every CTA then pays a
   // fence + atomic in its epilogue: measured 1.219 vs 1.203 ms kernel time at B64 x 32K, a wash overall)
-  static const bool inkernel = env_int_("VATTN_DECODE_COMBINE_INKERNEL", 0) != 0;
+  static const int inkernel_env = env_int_("VATTN_DECODE_COMBINE_INKERNEL", -1);
+  const bool inkernel = inkernel_env >= 0 ? inkernel_env != 0 : decode_small_problem(p);
   out->stream_k = allow_stream_k && decode_uses_stream_k(p);
   out->sk_ctas = stream_k_ctas();
   dp.arrive = (inkernel || out->stream_k) ? decode_arrive_counters(stream, (size_t)p.batch * p.num_kv_heads) : nullptr;

@@ -678,25 +678,11 @@ __device__ __forceinline__ float regs_quarter_max(const uint32_t (&r)[32], int k
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// 2^x on the FMA / ALU pipes instead of the 16-lane XU: round-to-nearest split x = n + f through the
-// 1.5 * 2^23 magic constant (n ends up in t's low mantissa bits), degree-3 polynomial for 2^f on
-// [-0.5, 0.5], n added into the exponent field.  Relative error <= 7.5e-5 (1.4e-4 at the -126 clamp),
-// checked against 2^x over [-126, 8] in float32 emulation -- a quarter of fp16's rounding step, a
-// sixtieth of bf16's, on values that are rounded to 16 bit right after.  9 issue slots against the
-// XU's 8 busy cycles per warp instruction: worth it for about one exponential in four.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -126.f);
-  const float t = x + 12582912.f;
-  const float f = x - (t - 12582912.f);
-  float p = fmaf(0.0551716086f, f, 0.242611118f);
-  p = fmaf(p, f, 0.693260997f);
-  p = fmaf(p, f, 0.999928074f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 // exponentials of one 32-column quarter, packed to 16 bit into out[0..15]; adds to the four partial sums.
-// POLY = 4: every fourth exponential goes through poly_exp2
-template <typename T, bool MASK, int POLY>
+// (Sending a fraction of them through a polynomial on the FMA pipe -- scalar, then packed FFMA2 pairs --
+// was measured twice and lost both times: 890 vs 974 and 879 vs 901 TFLOP/s at chunk 2048; the MUFU is
+// 52-55 % busy, it is the dependency chain S -> softmax -> P -> PV -> QK^T that paces the kernel.)
+template <typename T, bool MASK>
 __device__ __forceinline__ void regs_quarter_exp(const uint32_t (&r)[32], uint32_t* out, float scale_log2,
                                                  float mref, int key_base, int limit, float (&l)[4]) {
 #pragma unroll
@@ -705,7 +691,7 @@ __device__ __forceinline__ void regs_quarter_exp(const uint32_t (&r)[32], uint32
     float p1 = fast_exp2(fmaf(__uint_as_float(r[e + 1]), scale_log2, -mref));
     float p2 = fast_exp2(fmaf(__uint_as_float(r[e + 2]), scale_log2, -mref));
     const float x3 = fmaf(__uint_as_float(r[e + 3]), scale_log2, -mref);
-    float p3 = POLY == 4 ? poly_exp2(x3) : fast_exp2(x3);
+    float p3 = fast_exp2(x3);
     if (MASK) {
       const int k = key_base + e;
       if (k > limit) p0 = 0.f;
@@ -716,105 +702,6 @@ __device__ __forceinline__ void regs_quarter_exp(const uint32_t (&r)[32], uint32
     l[0] += p0, l[1] += p1, l[2] += p2, l[3] += p3;
     out[e / 2] = Elem<T>::from_f2(p0, p1);
     out[e / 2 + 1] = Elem<T>::from_f2(p2, p3);
-  }
-}
-
-// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2, one issue slot for two elements) + 3-input max ------
-// Measured on B200 (scripts/debug/pipe_throughput.cu): MUFU.EX2 16 / clk / SM in every format (f16x2 and
-// bf16x2 run at half the instruction rate, so they buy nothing), FFMA 128 / clk / SM, and the four
-// schedulers issue 128 thread-instructions / clk / SM in total.  A 128 x 128 score tile therefore costs
-// 1024 cycles of MUFU alone -- exactly the tensor-core time of its QK^T + PV -- so a softmax that sends
-// every exponential through the MUFU can at best tie with the MMAs.  MODE 2 takes ~3/8 of the
-// exponentials off the MUFU (degree-3 polynomial on the FMA pipe, the same constants as poly_exp2) and
-// halves the issue slots of everything else with packed pairs, FlashAttention-4's recipe.
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-
-// row max of one 32-column quarter, unmasked: 16 FMNMX3 in four independent chains
-__device__ __forceinline__ float regs_quarter_max3(const uint32_t (&r)[32]) {
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-  for (int e = 0; e < 32; e += 8) {
-    m0 = max3(m0, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-    m1 = max3(m1, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
-    m2 = max3(m2, __uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
-    m3 = max3(m3, __uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
-  }
-  return max3(fmaxf(m0, m1), m2, m3);
-}
-
-// 2^x for a packed pair on the FMA / ALU pipes (poly_exp2, two lanes at a time): clamp (2 FMNMX), split
-// x = n + f through the magic constant (3 packed adds), degree-3 Horner (3 FFMA2), n into the exponent
-// field (2 LEA)
-__device__ __forceinline__ uint64_t poly_exp2_x2(uint64_t x2) {
-  float xl, xh;
-  upk2(x2, xl, xh);
-  const uint64_t x = pk2(fmaxf(xl, -126.f), fmaxf(xh, -126.f));
-  const uint64_t magic = pk2(12582912.f, 12582912.f);
-  const uint64_t t = add2(x, magic);
-  const uint64_t f = sub2(x, sub2(t, magic));
-  uint64_t p = fma2(pk2(0.0551716086f, 0.0551716086f), f, pk2(0.242611118f, 0.242611118f));
-  p = fma2(p, f, pk2(0.693260997f, 0.693260997f));
-  p = fma2(p, f, pk2(0.999928074f, 0.999928074f));
-  float pl, ph, tl, th;
-  upk2(p, pl, ph);
-  upk2(t, tl, th);
-  return pk2(__int_as_float(__float_as_int(pl) + (__float_as_int(tl) << 23)),
-             __int_as_float(__float_as_int(ph) + (__float_as_int(th) << 23)));
-}
-
-// exponentials of one unmasked 32-column quarter, packed to 16 bit into out[0..15]; bit i of POLY_MASK
-// sends pair i of every 8 pairs through poly_exp2_x2 instead of the MUFU; row sums into two packed
-// accumulators
-template <typename T, uint32_t POLY_MASK>
-__device__ __forceinline__ void regs_quarter_exp_x2(const uint32_t (&r)[32], uint32_t* out, uint64_t scale2,
-                                                    uint64_t negm2, uint64_t (&l2)[2]) {
-#pragma unroll
-  for (int pr = 0; pr < 16; pr++) {
-    const uint64_t x = fma2(pk2u(r[2 * pr], r[2 * pr + 1]), scale2, negm2);
-    uint64_t p;
-    if ((POLY_MASK >> (pr & 7)) & 1u) {
-      p = poly_exp2_x2(x);
-    } else {
-      float xl, xh;
-      upk2(x, xl, xh);
-      p = pk2(fast_exp2(xl), fast_exp2(xh));
-    }
-    l2[pr & 1] = add2(l2[pr & 1], p);
-    float pl, ph;
-    upk2(p, pl, ph);
-    out[pr] = Elem<T>::from_f2(pl, ph);
   }
 }
 
@@ -1058,12 +945,12 @@ __device__ void prefill_work(const CUtensorMap* qmap, const CUtensorMap* kmap, c
 // S_t (16-bit packed) once they have been consumed, and the next QK^T into S_t is issued after
 // PV_t in program order (tcgen05.mma executes in issue order).
 //
-// One call handles key tiles [j0, j1) of one item (row-block pair, q head, batch entry).  The grid
-// kernel passes the whole range; the stream-K kernel (attn_prefill_tc.cu) cuts the flattened
-// (item, key tile) space into equal ranges per persistent CTA, so an item may be split into `parts`
-// segments: each publishes its un-normalised (O, m, l) and the last one to arrive reduces them
-// (the role of FA-2's split-KV kernel + combine, flash_fwd_kernel.h:503-1077,1115+, which the
-// reference needs for short chunks deep in a long context, flash_api.cpp:258-323).
+// One call handles key tiles [j0, j1) of one item (row-block pair, q head, batch entry).  When the
+// launch has too few items to fill the SMs evenly (256 items are 1.73 waves on 148 SMs; a 512-token
+// chunk has 64) the grid kernel splits every item into `parts` segments along the keys: each
+// publishes its un-normalised (O, m, l) and the last one to arrive reduces them -- the role of FA-2's
+// split-KV kernel + combine (flash_fwd_kernel.h:503-1077,1115+), which the reference needs for short
+// chunks deep in a long context (flash_api.cpp:258-323).
 constexpr int kPrefill2Threads = 384;
 constexpr int kPrefill2Stages = 4;
 constexpr uint32_t kCol2S = 0, kCol2O = 256;  // S_t at kCol2S + 128 t, O_t at kCol2O + 128 t
@@ -1080,11 +967,8 @@ struct PrefillSegment {
   // ---- parts > 1 only
   float* ws_o;         // [slot][2 blocks][128 rows][128] fp32, un-normalised
   float* ws_ml;        // [slot][2 blocks][128 rows][2]   (reference max in the log2 domain, row sum)
-  int64_t slot_base;   // slot of part c = slot_base + 2 * (first_cta + c) + (that CTA's range starts inside the item)
+  int64_t slot_base;   // slot of part c = slot_base + c (the grid kernel's split items)
   int64_t my_slot;
-  int first_cta;       // the parts are the CTAs first_cta .. first_cta + parts - 1
-  int64_t item_start;  // flattened index of the item's tile 0 (to recompute the other parts' slots)
-  StreamKPlan plan;
   int* arrive;         // arrival counter of this item (zero before and after the launch)
 };
 
@@ -1239,24 +1123,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
     float m_ref = -INFINITY, l = 0.f;
     const uint32_t s_addr = tmem + lane_base + kCol2S + t * kBN;
     const uint32_t o_addr = tmem + lane_base + kCol2O + t * kD;
-    // Ping-pong token (FlashAttention-3's scheduler barriers): the exponential pass of one warpgroup
-    // never overlaps the other's.  Left alone the two blocks lock IN phase -- the MMA thread issues
-    // PV0 QK0 PV1 QK1 back to back whenever both P tiles are ready, both S tiles come back together,
-    // both warpgroups then share the MUFU (2048 cycles for the pair) while the tensor pipe idles, and
-    // the period is ~4100 cycles for 2048 of MMA: ncu measured tensor 47 %, XU 52 %, softmax warps
-    // stalled on S 31 % of their samples.  With the token warpgroup 1 starts its exponentials when
-    // warpgroup 0 finishes, so block 0's PV / QK^T run under block 1's exponentials and vice versa.
-    // Named barriers 6 (token for block 0) and 7 (block 1), 128 waiters + 128 arrivers each; block 1
-    // hands out the first token and keeps its last one; a block with fewer tiles keeps passing it on.
-    const uint32_t tok_mine = 6 + t, tok_other = 6 + (t ^ 1);
-    if (t == 1 && n > 0) named_bar_arrive(6, 256);
-
-    for (int j = 0; j < n; j++) {
-      if (j >= my_n) {  // nothing left for this block: keep the token moving
-        named_bar_sync(tok_mine, 256);
-        if (t == 0 || j < n - 1) named_bar_arrive(tok_other, 256);
-        continue;
-      }
+    for (int j = 0; j < my_n; j++) {
       mbar_wait(&bar.s_full[t], j & 1);
       tc_fence_after();
       const int key0 = (j0 + j) * kBN;
@@ -1273,9 +1140,6 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         if (warp_mask)
           mx = fmaxf(fmaxf(regs_quarter_max<true>(s0, key0, limit), regs_quarter_max<true>(s1, key0 + 32, limit)),
                      fmaxf(regs_quarter_max<true>(s2, key0 + 64, limit), regs_quarter_max<true>(s3, key0 + 96, limit)));
-        else if constexpr (MODE == 2)
-          mx = fmaxf(fmaxf(regs_quarter_max3(s0), regs_quarter_max3(s1)),
-                     fmaxf(regs_quarter_max3(s2), regs_quarter_max3(s3)));
         else
           mx = fmaxf(fmaxf(regs_quarter_max<false>(s0, 0, 0), regs_quarter_max<false>(s1, 0, 0)),
                      fmaxf(regs_quarter_max<false>(s2, 0, 0), regs_quarter_max<false>(s3, 0, 0)));
@@ -1307,48 +1171,31 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       }
       l *= alpha;
       const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
-      named_bar_sync(tok_mine, 256);  // the MUFU is ours until the exponentials are done
       // P_t(j) overwrites the already consumed low half of S_t (in place)
       if constexpr (REGS) {
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t packed[32];
-        // pairs 1, 4 and 6 of every 8 (3/8 of the exponentials) leave the MUFU in MODE 2
-        constexpr uint32_t kPolyMask = 0x52;
-        uint64_t l2[2] = {0ull, 0ull};
-        const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), negm2 = pk2(-mref_safe, -mref_safe);
         if (warp_mask) {
-          regs_quarter_exp<T, true, 0>(s0, packed, p.scale_log2, mref_safe, key0, limit, ls);
-          regs_quarter_exp<T, true, 0>(s1, packed + 16, p.scale_log2, mref_safe, key0 + 32, limit, ls);
-        } else if constexpr (MODE == 2) {
-          regs_quarter_exp_x2<T, kPolyMask>(s0, packed, scale2, negm2, l2);
-          regs_quarter_exp_x2<T, kPolyMask>(s1, packed + 16, scale2, negm2, l2);
+          regs_quarter_exp<T, true>(s0, packed, p.scale_log2, mref_safe, key0, limit, ls);
+          regs_quarter_exp<T, true>(s1, packed + 16, p.scale_log2, mref_safe, key0 + 32, limit, ls);
         } else {
-          regs_quarter_exp<T, false, 0>(s0, packed, p.scale_log2, mref_safe, 0, 0, ls);
-          regs_quarter_exp<T, false, 0>(s1, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false>(s0, packed, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false>(s1, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
         }
         tmem_st_x32(s_addr, packed);  // keys 0..63 of P_t(j), 2 per column
         if (warp_mask) {
-          regs_quarter_exp<T, true, 0>(s2, packed, p.scale_log2, mref_safe, key0 + 64, limit, ls);
-          regs_quarter_exp<T, true, 0>(s3, packed + 16, p.scale_log2, mref_safe, key0 + 96, limit, ls);
-        } else if constexpr (MODE == 2) {
-          regs_quarter_exp_x2<T, kPolyMask>(s2, packed, scale2, negm2, l2);
-          regs_quarter_exp_x2<T, kPolyMask>(s3, packed + 16, scale2, negm2, l2);
+          regs_quarter_exp<T, true>(s2, packed, p.scale_log2, mref_safe, key0 + 64, limit, ls);
+          regs_quarter_exp<T, true>(s3, packed + 16, p.scale_log2, mref_safe, key0 + 96, limit, ls);
         } else {
-          regs_quarter_exp<T, false, 0>(s2, packed, p.scale_log2, mref_safe, 0, 0, ls);
-          regs_quarter_exp<T, false, 0>(s3, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false>(s2, packed, p.scale_log2, mref_safe, 0, 0, ls);
+          regs_quarter_exp<T, false>(s3, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
         }
         tmem_st_x32(s_addr + 32, packed);  // keys 64..127
-        {
-          float a0, a1, b0, b1;
-          upk2(l2[0], a0, a1);
-          upk2(l2[1], b0, b1);
-          l += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((a0 + a1) + (b0 + b1));
-        }
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       } else {
         l += warp_mask ? tile_exp_store<T, true>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit)
                        : tile_exp_store<T, false>(s_addr, s_addr, p.scale_log2, mref_safe, key0, limit);
       }
-      if (t == 0 || j < n - 1) named_bar_arrive(tok_other, 256);
       tmem_wait_st();
       if ((j0 + j + 1) * kBN > lk) {
         const int pv = 2 * j + 1;
@@ -1427,15 +1274,13 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         __threadfence();
         float M = -INFINITY;
         for (int c = 0; c < seg.parts; c++) {
-          const int cta = seg.first_cta + c;
-          const int64_t sl = seg.slot_base + 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+          const int64_t sl = seg.slot_base + c;
           M = fmaxf(M, __ldcg(seg.ws_ml + ((sl * 2 + t) * kBM + i) * 2));
         }
         const float Ms = (M == -INFINITY) ? 0.f : M;
         float L = 0.f;
         for (int c = 0; c < seg.parts; c++) {
-          const int cta = seg.first_cta + c;
-          const int64_t sl = seg.slot_base + 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+          const int64_t sl = seg.slot_base + c;
           const int64_t row = (sl * 2 + t) * kBM + i;
           const float lc = __ldcg(seg.ws_ml + row * 2 + 1);
           if (lc > 0.f) L = fmaf(lc, fast_exp2(__ldcg(seg.ws_ml + row * 2) - Ms), L);
@@ -1447,8 +1292,7 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
 #pragma unroll
           for (int e = 0; e < kD / 2; e++) acc[e] = 0.f;
           for (int c = 0; c < seg.parts; c++) {
-            const int cta = seg.first_cta + c;
-            const int64_t sl = seg.slot_base + 2 * cta + (sk_range_begin(seg.plan, cta) >= seg.item_start ? 0 : 1);
+            const int64_t sl = seg.slot_base + c;
             const int64_t row = (sl * 2 + t) * kBM + i;
             if (!(__ldcg(seg.ws_ml + row * 2 + 1) > 0.f)) continue;  // empty part: its O row was never written
             const float w = fast_exp2(__ldcg(seg.ws_ml + row * 2) - Ms);
