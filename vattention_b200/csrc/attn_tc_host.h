@@ -23,6 +23,7 @@ bool decode_tc_fuses_append(const vattn_fwd_params_t& p);
 struct PrefillTcLaunch {
   tcwork::PrefillParams pp;
   CUtensorMap qmap, kmap, vmap, kmap_tail, vmap_tail;
+  CUtensorMap kmap64, vmap64;  // 64-row boxes (prefill3)
 };
 void build_prefill_tc(const vattn_fwd_params_t& p, PrefillTcLaunch* out);
 
