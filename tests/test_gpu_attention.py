@@ -363,11 +363,8 @@ def test_pod_fused_many_items_matches_oracle(dtype, fused_params):
     sep_p = att.flash_attn_with_kvcache(d(q_p), d(kc_p), d(vc_p), cache_seqlens=d(lens_p), causal=True)
     sep_d = att.flash_attn_with_kvcache(d(q_d), kd, vd, d(kn), d(vn), cache_seqlens=d(lens_d),
                                         cache_batch_idx=d(idx), causal=True)  # re-appends the same rows
-    if fused_params == 15:
-        assert torch.equal(out_p, sep_p) and torch.equal(out_d, sep_d)
-    else:
-        close(out_p, sep_p, dtype)
-        close(out_d, sep_d, dtype)
+    close(out_p, sep_p, dtype)   # (bit for bit only when the call launches the very same kernels)
+    close(out_d, sep_d, dtype)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])

@@ -396,6 +396,19 @@ PodStrategy pod_strategy(int32_t fused_params) {
   if (fused_params == 64) return PodStrategy::Dual;  // our own value: none of the reference's configurations
   return fused_params == 15 ? PodStrategy::Streams : PodStrategy::Kernel;
 }
+
+// fused_params == 15 ("pick the most suitable", fused_api.cpp:24-53): the dual-role kernel when the two
+// sides are of comparable length, otherwise the two specialised kernels.  Time estimates from the
+// shapes: prefill 4 Hq D Bp Sq Sk FLOP at ~0.9 PFLOP/s, decode 4 Hkv D Bd Sk bytes at ~6.9 TB/s.
+// Measured (Llama-3-8B fp16, profiles/r2_pod_arms.jsonl): 1 x 2048 @ 16K + 64 x 16K decodes, ratio ~1:
+// dual 1.081 ms vs 1.264 serial / 1.263 two streams / 1.359 persistent; 8 x 16K + 56 x 4K, ratio ~70:
+// dual 20.1 ms vs 17.0 serial -- the decode side has nothing to hide behind there.
+bool pod_auto_prefers_dual(const vattn_fwd_params_t& pre, const vattn_fwd_params_t& dec) {
+  const double tp = 4.0 * pre.num_heads * pre.head_dim * (double)pre.batch * pre.seqlen_q * pre.seqlen_k / 0.9e15;
+  const double td = 4.0 * dec.num_kv_heads * dec.head_dim * (double)dec.batch * dec.seqlen_k / 6.9e12;
+  const double lo = tp < td ? tp : td, hi = tp < td ? td : tp;
+  return hi > 0 && lo / hi >= 0.3;
+}
 }  // namespace
 
 int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* decode,
@@ -406,7 +419,10 @@ int vattn_pod_fwd(const vattn_fwd_params_t* prefill, const vattn_fwd_params_t* d
     if ((prefill && prefill->rotary_cos) || (decode && decode->rotary_cos))
       throw UnsupportedError("[vattn] the fused POD call takes no rotary arguments (fused_attn_interface.py:12-40)");
     cudaStream_t main = static_cast<cudaStream_t>(stream);
-    const PodStrategy strat = pod_strategy(fused_params);
+    PodStrategy strat = pod_strategy(fused_params);
+    if (fused_params == 15 && !std::getenv("VATTN_POD_STRATEGY") && pod_fused_path(prefill, decode) &&
+        pod_auto_prefers_dual(*prefill, *decode))
+      strat = PodStrategy::Dual;
     if (strat == PodStrategy::Kernel && pod_fused_path(prefill, decode)) {
       launch_pod_tc(*prefill, *decode, workspace, workspace_bytes, main);
       return VATTN_OK;
