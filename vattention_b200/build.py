@@ -53,7 +53,15 @@ def _compile(src: Path, hdr_mtime: float, force: bool, verbose: bool) -> Path:
     return obj
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
+def build_library(force: bool = False, verbose: bool = False, watchdog: bool = False) -> Path:
+    """watchdog=True builds libvattn_b200_dbg.so (-DVATTN_WATCHDOG: mbarrier waits that never complete
+    print the barrier and trap instead of hanging); load it with VATTN_B200_LIB=<path>."""
+    global OBJ_DIR, LIB_PATH
+    if watchdog:
+        OBJ_DIR = REPO / "build" / "obj_dbg"
+        LIB_PATH = PKG_DIR / "libvattn_b200_dbg.so"
+        if "-DVATTN_WATCHDOG" not in COMMON:
+            COMMON.append("-DVATTN_WATCHDOG")
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
     srcs = _sources()
     hdr_mtime = _headers_mtime()
@@ -73,5 +81,5 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    p = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    p = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, watchdog="--watchdog" in sys.argv)
     print(p)

@@ -92,7 +92,7 @@ struct TcBarriers {
   uint64_t full[kMaxStages], empty[kMaxStages];  // TMA ring
   uint64_t q_full;                               // prefill: Q block landed
   uint64_t s_full[2], p_ready[2];                // S ready for softmax / P ready for the PV MMA
-  uint64_t s_full_b[2];                          // prefill3: second S buffer of each row block
+  uint64_t s_full_b[2], p_ready_b[2], o_full_b[2];  // prefill3: odd key tiles (second S buffer) of each row block
   uint64_t o_full[2];                            // decode: O_j^T ready; prefill uses [0] as "PV_j done"
   int ticket;                                    // split items: arrival order of this part (prefill stream-K)
 };
@@ -1422,7 +1422,9 @@ __device__ void prefill3_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
       mbar_reinit(&bar.s_full[i], 1, barriers_live);
       mbar_reinit(&bar.s_full_b[i], 1, barriers_live);
       mbar_reinit(&bar.p_ready[i], 128, barriers_live);
+      mbar_reinit(&bar.p_ready_b[i], 128, barriers_live);
       mbar_reinit(&bar.o_full[i], 1, barriers_live);
+      mbar_reinit(&bar.o_full_b[i], 1, barriers_live);
     }
     fence_mbar_init();
   }
@@ -1474,14 +1476,19 @@ __device__ void prefill3_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         umma_commit((j & 1) ? &bar.s_full_b[t] : &bar.s_full[t]);
       };
       auto issue_pv = [&](int t, int j, uint32_t v0) {  // O_t += P_t(j) . V_j
-        mbar_wait(&bar.p_ready[t], j & 1);
+        // Even and odd tiles signal on separate barriers.  A warpgroup may finish tile j+1 before this
+        // thread has looked at tile j (S(j+1) comes from the prologue or from behind PV(j-1)); with one
+        // barrier both phases would complete and the parity wait for tile j would then see an even
+        // number of phases and wait for tile j+2 -- whose S needs PV(j).  Per buffer the producer can
+        // never be two phases ahead: tile j+2 needs QK^T(j+2), issued behind PV(j).
+        mbar_wait((j & 1) ? &bar.p_ready_b[t] : &bar.p_ready[t], (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < kBN / 16; ks++)
           umma_ts(tmem + kCol3O + t * kD, tmem + t * 128 + (j & 1) * kBN + ks * 8,
                   make_smem_desc(v0 + ks * (16 * 128), kBN * 128, 1024, kLayoutSw128), p.idesc_pv,
                   (j > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&bar.o_full[t]);  // completes phase j of block t
+        umma_commit((j & 1) ? &bar.o_full_b[t] : &bar.o_full[t]);  // phase j >> 1 of that barrier
       };
       for (int jj = 0; jj < 2 && jj < n; jj++) {  // prologue: S_t(0), S_t(1) into the two buffers
         const int s = wait_slot();
@@ -1562,8 +1569,10 @@ __device__ void prefill3_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         m_ref = mx;
       }
       if (__any_sync(0xffffffffu, grow) && j > 0) {
-        // O must hold every earlier tile before it is rescaled: S_t(j) only proves PV_t(j-2) retired
-        mbar_wait(&bar.o_full[t], (j - 1) & 1);
+        // O must hold every earlier tile before it is rescaled: S_t(j) only proves PV_t(j-2) retired.
+        // (PV_t(j-3) is known complete -- S_t(j-1) was ready -- so the barrier of tile j-1's parity is
+        // at most one phase behind: the wait is unambiguous)
+        mbar_wait(((j - 1) & 1) ? &bar.o_full_b[t] : &bar.o_full[t], ((j - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < kD; c += 32) {
@@ -1605,14 +1614,13 @@ __device__ void prefill3_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
         fence_proxy_async_smem();
       }
       tc_fence_before();
-      mbar_arrive(&bar.p_ready[t]);
+      mbar_arrive((j & 1) ? &bar.p_ready_b[t] : &bar.p_ready[t]);
     }
 
     if (my_n > 0) {
-      // S_t(my_n - 1) only proves PV_t(my_n - 3) retired: wait for the last two phases in order (a
-      // parity wait for the last one alone could be satisfied by the stale phase my_n - 3)
-      if (my_n > 1) mbar_wait(&bar.o_full[t], (my_n - 2) & 1);
-      mbar_wait(&bar.o_full[t], (my_n - 1) & 1);
+      // the last two PVs, one on each barrier (each is at most one phase behind, see above)
+      if (my_n > 1) mbar_wait(((my_n - 2) & 1) ? &bar.o_full_b[t] : &bar.o_full[t], ((my_n - 2) >> 1) & 1);
+      mbar_wait(((my_n - 1) & 1) ? &bar.o_full_b[t] : &bar.o_full[t], ((my_n - 1) >> 1) & 1);
       tc_fence_after();
     }
     prefill_block_epilogue<T>(p, seg, bar, tmem, o_addr, t, i, qi, h, b, rows[t], my_n, m_ref, l);

@@ -3,6 +3,7 @@
 // descriptors.  Bit layouts follow the PTX ISA's tcgen05 descriptor tables (the same
 // fields CUTLASS names in cute/arch/mma_sm100_desc.hpp).
 #pragma once
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,8 +41,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef VATTN_WATCHDOG
+  // debug build (python -m vattention_b200.build --watchdog -> libvattn_b200_dbg.so): a wait that never
+  // completes reports which barrier (its shared-memory address; the barrier blocks sit at a 1024-byte
+  // aligned offset, so addr % 1024 is the offset inside TcBarriers) and traps instead of hanging the GPU
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++) {
+    if (spins == (1u << 20))  // report, keep waiting so that every stuck thread gets to report
+      printf("[vattn watchdog] block (%d,%d,%d) thread %d stuck on mbarrier smem 0x%x (offset %u) parity %u\n",
+             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), smem_u32(bar) & 1023u, parity);
+    if (spins == (1u << 23)) __trap();
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tensor core reads)
