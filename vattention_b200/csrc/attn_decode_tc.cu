@@ -77,125 +77,6 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
 }
 
 
-// ---- stream-K persistent variant --------------------------------------------------------------
-// grid = 2 x SMs persistent CTAs; the split of the flattened (batch, kv head, key tile) space is
-// computed ON THE DEVICE from cache_seqlens (attn_tc_work.cuh: StreamKPlan), so the launch shape and the
-// workspace depend neither on the actual lengths nor on the extent of the cache view (the wrappers of
-// the fi / POD backends pass the whole virtual tensor), every CTA streams the same number of tiles
-// (no tail wave, no per-chunk prologue), and the partials of a sequence that spans several CTAs are
-// reduced inside the kernel by the last part to arrive: one launch per decode call.
-// Replaces the role of num_splits_heuristic + the combine kernel (pod_attn/pod_attn/flash_api.cpp:258-323,
-// flash_fwd_kernel.h:1115+).
-template <int STAGES>
-struct __align__(1024) DecodeSkSmemT {
-  DecodeSmemT<STAGES> data;
-  TcBarriers bar;
-  uint32_t tmem_base;
-  int warp_sum[8];
-  int total_vt, start_b, start_prefix;
-};
-
-template <typename T, int GP, int STAGES = kStages>
-__global__ void __launch_bounds__(kThreads, 2)
-decode_sk_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
-                 const __grid_constant__ CUtensorMap kmap_tail, const __grid_constant__ CUtensorMap vmap_tail,
-                 const DecodeTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  DecodeSkSmemT<STAGES>& sm =
-      *reinterpret_cast<DecodeSkSmemT<STAGES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool fused_new = p.k_new != nullptr;
-  auto seq_len = [&](int b) {
-    return (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + (fused_new ? 0 : p.seqlen_new);
-  };
-  auto vtiles = [&](int len) { return max(1, (len + kTile - 1) / kTile); };
-
-  // ---- virtual tiles per batch entry: block-wide exclusive scan, thread t owns a run of entries
-  const int per = (p.batch + kThreads - 1) / kThreads;
-  const int i0 = min(p.batch, (int)threadIdx.x * per), i1 = min(p.batch, i0 + per);
-  int mine = 0;
-  for (int i = i0; i < i1; i++) mine += vtiles(seq_len(i));
-  int incl = mine;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, off);
-    if (lane >= off) incl += v;
-  }
-  if (lane == 31) sm.warp_sum[warp] = incl;
-  __syncthreads();
-  int before = incl - mine;
-  for (int w = 0; w < warp; w++) before += sm.warp_sum[w];
-  if (threadIdx.x == kThreads - 1) sm.total_vt = before + mine;
-  __syncthreads();
-  StreamKPlan pl;
-  pl.total = (int64_t)sm.total_vt * p.num_kv_heads;
-  pl.ctas = gridDim.x;
-  pl.q = pl.total / pl.ctas;
-  pl.r = (int)(pl.total % pl.ctas);
-  const int cta = blockIdx.x;
-  const int64_t lo = sk_range_begin(pl, cta);
-  const int64_t hi = lo + pl.q + (cta < pl.r ? 1 : 0);
-  if (lo >= hi) return;  // CTA-uniform; nothing allocated yet
-  {
-    // the thread whose run contains tile `lo` finds the batch entry the range starts in
-    const int64_t t_lo = (int64_t)before * p.num_kv_heads, t_hi = (int64_t)(before + mine) * p.num_kv_heads;
-    if (lo >= t_lo && lo < t_hi) {
-      int pre = before, b = i0;
-      for (; b < i1; b++) {
-        const int vt = vtiles(seq_len(b));
-        if (lo < (int64_t)(pre + vt) * p.num_kv_heads) break;
-        pre += vt;
-      }
-      sm.start_b = b, sm.start_prefix = pre;
-    }
-  }
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&kmap);
-    prefetch_tensormap(&vmap);
-  }
-  if (warp == 2) {
-    tmem_alloc(&sm.tmem_base, kDecodeTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sm.tmem_base;
-
-  int b = sm.start_b;
-  int64_t pre = sm.start_prefix;
-  bool live = false;
-  for (int64_t x = lo; x < hi;) {
-    const int len = seq_len(b);
-    const int vt = vtiles(len);
-    const int ntiles = (len + kTile - 1) / kTile;
-    const int64_t seq_base = pre * p.num_kv_heads;
-    const int hkv = (int)((x - seq_base) / vt);
-    const int64_t seq_start = seq_base + (int64_t)hkv * vt, seq_end = seq_start + vt;
-    const int64_t seg_end = hi < seq_end ? hi : seq_end;
-    DecodeSegment seg;
-    seg.b = b, seg.hkv = hkv, seg.len = len;
-    seg.tile0 = (int)(x - seq_start);
-    seg.n = max(0, min((int)(seg_end - x), ntiles - seg.tile0));
-    seg.owns_new = fused_new && seg_end == seq_end;
-    const int first_cta = sk_cta_of(pl, seq_start), last_cta = sk_cta_of(pl, seq_end - 1);
-    seg.parts = last_cta - first_cta + 1;
-    const int64_t ordinal = (int64_t)b * p.num_kv_heads + hkv;
-    seg.part_idx = (cta + ordinal) * p.group, seg.part_stride_g = 1;
-    seg.red_idx = (first_cta + ordinal) * p.group, seg.red_stride_g = 1, seg.red_stride_c = p.group;
-    seg.publish_empty = false;
-    decode_segment<T, GP, STAGES>(&kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, tmem, seg, live);
-    live = true;
-    x = seg_end;
-    if (x == seq_base + (int64_t)vt * p.num_kv_heads) {
-      pre += vt;
-      b++;
-    }
-  }
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, kDecodeTmemCols);
-}
-
 int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return v ? std::atoi(v) : dflt;
@@ -228,25 +109,12 @@ int tiles_per_chunk_for(const vattn_fwd_params_t& p) {
   return (int)tpc;
 }
 
-// Schedules.  Default: the (chunk, kv head, batch) grid + combine kernel -- the hardware block scheduler
-// balances dynamically, measured faster everywhere (B200, bf16, one layer-call incl. append, grid vs
-// stream-K: B64 x Hkv8 x 32K 1.196 vs 1.216 ms; B64 x Hkv1 x 32K 0.168 vs 0.174; B16 x Hkv1 x 32K
-// 0.083 vs 0.100; 128K 0.189 vs 0.203).  VATTN_DECODE_SCHED=streamk selects the persistent stream-K
-// kernel (device-side split, in-kernel reduction, ONE launch whose shape and workspace do not depend
-// on the lengths or on the extent of the cache view).
-bool decode_uses_stream_k(const vattn_fwd_params_t& p) {
-  static const bool sk = [] {
-    const char* e = std::getenv("VATTN_DECODE_SCHED");
-    return e && std::string(e) == "streamk";
-  }();
-  return sk && p.num_splits <= 0;
-}
-int stream_k_ctas() { return num_sms() * 2; }
-size_t stream_k_workspace(const vattn_fwd_params_t& p) {
-  // one partial slot per (persistent CTA + sequence ordinal): group x (D + 2) floats each
-  const size_t slots = (size_t)stream_k_ctas() + (size_t)p.batch * p.num_kv_heads;
-  return slots * (p.num_heads / p.num_kv_heads) * (kHeadDim + 2) * sizeof(float);
-}
+// (A persistent stream-K schedule -- the flattened (batch, kv head, tile) space cut into equal ranges
+// per CTA on the device, partials reduced by the last part to arrive, one launch -- was built and
+// measured in round 2 and lost to this grid everywhere: B64 x Hkv8 x 32K 1.216 vs 1.196 ms, B64 x Hkv1
+// x 32K 0.174 vs 0.168, B16 x Hkv1 x 32K 0.100 vs 0.083, 128K 0.203 vs 0.189; ncu showed one straggler
+// SM at 2x the mean (profiles/r2_decode_small_streamk_ncu_raw.csv).  The block scheduler's dynamic
+// balance beats a static equal split; removed.)
 
 int num_chunks_for(const vattn_fwd_params_t& p) {
   const int nt = (p.seqlen_k + kTile - 1) / kTile;
@@ -260,21 +128,6 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
   const int group = p.num_heads / p.num_kv_heads;
   DecodeTcLaunch L;
   build_decode_tc(p, ws, stream, &L, true);
-  if (L.stream_k) {
-    const size_t smem = sizeof(DecodeSkSmemT<kStages>) + 1024;
-    auto launch_sk = [&](auto kernel) {
-      VATTN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int tslot = timing_begin(stream);
-      kernel<<<L.sk_ctas, kThreads, smem, stream>>>(L.kmap, L.vmap, L.kmap_tail, L.vmap_tail, L.dp);
-      timing_end(tslot, stream);
-    };
-    if (group <= 4) launch_sk(decode_sk_kernel<T, 4>);
-    else if (group <= 8) launch_sk(decode_sk_kernel<T, 8>);
-    else launch_sk(decode_sk_kernel<T, 16>);
-    count_launch();
-    VATTN_CUDA(cudaGetLastError());
-    return;
-  }
   const size_t smem = sizeof(DecodeKernelSmem) + 1024;
   dim3 grid(L.dp.num_chunks, p.num_kv_heads, p.batch);
   auto launch = [&](auto kernel) {
@@ -308,8 +161,7 @@ int* decode_arrive_counters(cudaStream_t stream, size_t need) { return arrival_c
 
 bool decode_tc_fuses_append(const vattn_fwd_params_t& p) { return p.k_new != nullptr && p.seqlen_new == 1; }
 
-void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream, DecodeTcLaunch* out,
-                     bool allow_stream_k) {
+void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream, DecodeTcLaunch* out, bool) {
   const int group = p.num_heads / p.num_kv_heads;
   const int eb = 2;
   DecodeTcParams& dp = out->dp;
@@ -339,9 +191,7 @@ void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream,
   // measured (B16 x Hkv1 x 32K, one wave of 288 CTAs): separate combine kernel 72.8 us, in-kernel 87.0 us
   // -- every CTA pays a fence + atomic in its epilogue; the default stays the combine kernel
   const bool inkernel = inkernel_env > 0;
-  out->stream_k = allow_stream_k && decode_uses_stream_k(p);
-  out->sk_ctas = stream_k_ctas();
-  dp.arrive = (inkernel || out->stream_k) ? decode_arrive_counters(stream, (size_t)p.batch * p.num_kv_heads) : nullptr;
+  dp.arrive = inkernel ? decode_arrive_counters(stream, (size_t)p.batch * p.num_kv_heads) : nullptr;
   dp.tiles_per_chunk = tiles_per_chunk_for(p);
   dp.num_chunks = num_chunks_for(p);
   dp.scale_log2 = p.softmax_scale * kLog2e;
@@ -352,13 +202,7 @@ void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream,
   // 8-key groups (verified on device by vattn_selftest_umma).
   dp.v_lbo = kTile * 128, dp.v_sbo = 1024;
   out->ws = SplitWorkspace{nullptr, nullptr};
-  if (out->stream_k) {
-    const size_t slots = (size_t)out->sk_ctas + (size_t)p.batch * p.num_kv_heads;
-    out->ws.acc = static_cast<float*>(ws);
-    out->ws.ml = out->ws.acc + slots * group * kHeadDim;
-  } else if (dp.num_chunks > 1) {
-    out->ws = carve_workspace(ws, p.batch, p.num_heads, dp.num_chunks, kHeadDim);
-  }
+  if (dp.num_chunks > 1) out->ws = carve_workspace(ws, p.batch, p.num_heads, dp.num_chunks, kHeadDim);
   dp.ws_acc = out->ws.acc, dp.ws_ml = out->ws.ml;
   out->kmap = make_headdim128_map(p.k_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.k_row_stride * eb,
                                   p.k_head_stride * eb, p.k_batch_stride * eb, kTile);
@@ -400,9 +244,7 @@ size_t decode_tc_workspace_grid(const vattn_fwd_params_t& p) {
   return c > 1 ? split_workspace_bytes(p.batch, p.num_heads, c, kHeadDim) : 0;
 }
 
-size_t decode_tc_workspace(const vattn_fwd_params_t& p) {
-  return decode_uses_stream_k(p) ? stream_k_workspace(p) : decode_tc_workspace_grid(p);
-}
+size_t decode_tc_workspace(const vattn_fwd_params_t& p) { return decode_tc_workspace_grid(p); }
 
 void launch_decode_tc(const vattn_fwd_params_t& p, void* ws, size_t, cudaStream_t stream) {
   if (p.dtype == VATTN_DTYPE_BF16) launch_t<__nv_bfloat16>(p, ws, stream);

@@ -154,60 +154,6 @@ prefill2_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-// 64-key tiles, two S buffers per row block (prefill3_work): same grid and split arguments
-struct __align__(1024) Prefill3KernelSmem {
-  Prefill3Smem data;
-  TcBarriers bar;
-  uint32_t tmem_base;
-};
-
-template <typename T>
-__global__ void __launch_bounds__(kPrefill2Threads, 1)
-prefill3_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
-                   const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap kmap_tail,
-                   const __grid_constant__ CUtensorMap vmap_tail, const PrefillParams p, const PrefillSplitArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  Prefill3KernelSmem& sm =
-      *reinterpret_cast<Prefill3KernelSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
-  const int pairs = (p.num_m_tiles + 1) / 2;
-  PrefillSegment seg{};
-  seg.mt2 = pairs - 1 - (int)(blockIdx.x / a.splits), seg.h = blockIdx.y, seg.b = blockIdx.z;
-  seg.j0 = 0, seg.j1 = INT_MAX, seg.parts = 1;
-  if (a.splits > 1) {
-    const int part = (int)(blockIdx.x % a.splits);
-    const int lk = (p.cache_seqlens ? p.cache_seqlens[seg.b] : p.seqlen_k) + p.seqlen_new;
-    int m0[2], rows[2], nt[2];
-    prefill_pair_tiles(p, lk, seg.mt2, m0, rows, nt);  // 128-key units: the split points stay tile aligned
-    const int n = max(nt[0], nt[1]);
-    const int parts = max(1, min(a.splits, n / kMinTilesPerSplit));
-    if (part >= parts) return;
-    const int per = (n + parts - 1) / parts;
-    seg.j0 = part * per, seg.j1 = min(n, seg.j0 + per);
-    seg.parts = parts;
-    const int64_t item = ((int64_t)seg.b * p.num_heads + seg.h) * pairs + (blockIdx.x / a.splits);
-    seg.ws_o = a.ws_o, seg.ws_ml = a.ws_ml;
-    seg.slot_base = item * a.splits;
-    seg.my_slot = seg.slot_base + part;
-    seg.arrive = a.arrive + item;
-  }
-  if (warp == 0 && (threadIdx.x & 31) == 0) {
-    prefetch_tensormap(&qmap);
-    prefetch_tensormap(&kmap);
-    prefetch_tensormap(&vmap);
-  }
-  if (warp == 2) {
-    tmem_alloc(&sm.tmem_base, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  prefill3_work<T>(&qmap, &kmap, &vmap, &kmap_tail, &vmap_tail, p, sm.data, sm.bar, sm.tmem_base, seg, false);
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(sm.tmem_base, 512);
-}
-
 int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return v ? std::atoi(v) : dflt;
@@ -260,17 +206,9 @@ void launch_t(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream) {
       a.ws_ml = a.ws_o + (size_t)items * splits * 2 * kBM * kD;
     }
     dim3 grid(pairs * splits, p.num_heads, p.batch);
-    static const int which = env_int("VATTN_PREFILL_KERNEL", 2);
-    if (which == 3) {
-      const size_t smem3 = sizeof(Prefill3KernelSmem) + 1024;
-      VATTN_CUDA(cudaFuncSetAttribute(prefill3_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-      prefill3_tc_kernel<T><<<grid, kPrefill2Threads, smem3, stream>>>(L.qmap, L.kmap64, L.vmap64, L.kmap_tail,
+    VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prefill2_tc_kernel<T, 1><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
                                                                        L.vmap_tail, L.pp, a);
-    } else {
-      VATTN_CUDA(cudaFuncSetAttribute(prefill2_tc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prefill2_tc_kernel<T, 1><<<grid, kPrefill2Threads, smem, stream>>>(L.qmap, L.kmap, L.vmap, L.kmap_tail,
-                                                                         L.vmap_tail, L.pp, a);
-    }
   } else {
     const size_t smem = sizeof(PrefillKernelSmem) + 1024;
     VATTN_CUDA(cudaFuncSetAttribute(prefill_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -311,11 +249,6 @@ void build_prefill_tc(const vattn_fwd_params_t& p, PrefillTcLaunch* out) {
                                   p.k_head_stride * eb, p.k_batch_stride * eb, kBN);
   out->vmap = make_headdim128_map(p.v_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.v_row_stride * eb,
                                   p.v_head_stride * eb, p.v_batch_stride * eb, kBN);
-  pp.idesc_qk64 = make_idesc(fmt, kBM, kBN3, 0, 0);
-  out->kmap64 = make_headdim128_map(p.k_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.k_row_stride * eb,
-                                    p.k_head_stride * eb, p.k_batch_stride * eb, kBN3);
-  out->vmap64 = make_headdim128_map(p.v_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.v_row_stride * eb,
-                                    p.v_head_stride * eb, p.v_batch_stride * eb, kBN3);
   const int rk = safe_tail_rows(p.k_row_stride * eb), rv = safe_tail_rows(p.v_row_stride * eb);
   pp.tail_rows = rk < rv ? rk : rv;
   out->kmap_tail = make_headdim128_map(p.k_cache, p.seqlen_k, p.num_kv_heads, p.cache_batch, p.k_row_stride * eb,

@@ -10,20 +10,16 @@ struct DecodeTcLaunch {
   tcwork::DecodeTcParams dp;
   CUtensorMap kmap, vmap, kmap_tail, vmap_tail;
   SplitWorkspace ws;
-  bool stream_k = false;  // device-side stream-K schedule (decode_sk_kernel) instead of the chunk grid
-  int sk_ctas = 0;
 };
 // fills kernel parameters + TMA maps for a seqlen_q == 1 problem; `ws` receives the split partials
-// (allow_stream_k = false: the classic chunk grid's parameters, as the POD kernel's decode items use them)
 void build_decode_tc(const vattn_fwd_params_t& p, void* ws, cudaStream_t stream, DecodeTcLaunch* out,
-                     bool allow_stream_k);
+                     bool unused = false);
 // true when the decode kernel itself appends k_new/v_new (one new token per sequence)
 bool decode_tc_fuses_append(const vattn_fwd_params_t& p);
 
 struct PrefillTcLaunch {
   tcwork::PrefillParams pp;
   CUtensorMap qmap, kmap, vmap, kmap_tail, vmap_tail;
-  CUtensorMap kmap64, vmap64;  // 64-row boxes (prefill3)
 };
 void build_prefill_tc(const vattn_fwd_params_t& p, PrefillTcLaunch* out);
 

@@ -87,12 +87,11 @@ __device__ __forceinline__ void load_kv_tile(uint8_t* dst, const CUtensorMap* fu
 
 // mbarriers of one CTA; shared by both kinds of work so that a persistent CTA alternating between
 // them re-initialises the same, never-overwritten words
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 6;
 struct TcBarriers {
   uint64_t full[kMaxStages], empty[kMaxStages];  // TMA ring
   uint64_t q_full;                               // prefill: Q block landed
   uint64_t s_full[2], p_ready[2];                // S ready for softmax / P ready for the PV MMA
-  uint64_t s_full_b[2], p_ready_b[2], o_full_b[2];  // prefill3: odd key tiles (second S buffer) of each row block
   uint64_t o_full[2];                            // decode: O_j^T ready; prefill uses [0] as "PV_j done"
   int ticket;                                    // split items: arrival order of this part (prefill stream-K)
 };
@@ -141,8 +140,7 @@ struct __align__(1024) DecodeSmemT {
 
 // One contiguous run of key tiles of one (batch entry, kv head): what a CTA processes between two
 // (re)initialisations of its pipeline.  The classic grid makes one segment per (chunk, kv head, batch)
-// CTA; the stream-K schedule cuts the flattened tile space into equal ranges per persistent CTA and a
-// range contributes one segment per sequence it touches.
+// CTA.
 struct DecodeSegment {
   int b, hkv;
   int tile0, n;        // first key tile, number of key tiles (0: only the appended token, or nothing)
@@ -540,29 +538,6 @@ __device__ void decode_work(const CUtensorMap* kmap, const CUtensorMap* vmap, co
   decode_segment<T, GP, STAGES>(kmap, vmap, kmap_tail, vmap_tail, p, sm, bar, tmem, seg, barriers_live, sd);
 }
 
-// ---- stream-K schedule over the flattened (batch, kv head, key tile) space ---------------------
-// Every sequence contributes max(1, ceil(len / 128)) virtual tiles per kv head (a sequence with no
-// cached rows still needs its output written), batch-major.  G persistent CTAs cut the T virtual
-// tiles into G equal ranges (the first T mod G one tile longer); a range contributes one segment per
-// sequence it touches.  Segment ids `cta + sequence ordinal` are unique and increase along the tile
-// axis, so the parts of one sequence occupy consecutive partial slots; the last part to arrive
-// reduces them (p.arrive).  All of it is computed on the device from cache_seqlens: the launch
-// shape depends neither on the lengths nor on the extent of the cache view.
-struct StreamKPlan {
-  int64_t total;   // T
-  int64_t q;       // T / G
-  int r;           // T % G
-  int ctas;        // G
-};
-__device__ __forceinline__ int64_t sk_range_begin(const StreamKPlan& pl, int c) {
-  return (int64_t)c * pl.q + (c < pl.r ? c : pl.r);
-}
-__device__ __forceinline__ int sk_cta_of(const StreamKPlan& pl, int64_t x) {
-  const int64_t big = (int64_t)pl.r * (pl.q + 1);
-  if (x < big) return (int)(x / (pl.q + 1));
-  return pl.r + (int)((x - big) / pl.q);  // q > 0 here: x >= big implies tiles remain for the short ranges
-}
-
 // ======================================================================= prefill ====
 constexpr int kPrefillStages = 5;
 constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;  // TMEM columns: S x2 | O | P x2 (packed)
@@ -580,7 +555,6 @@ struct PrefillParams {
   uint32_t idesc_qk, idesc_pv;
   uint32_t v_lbo, v_sbo;
   int tail_rows;
-  uint32_t idesc_qk64;  // prefill3: QK^T with 64 keys on the MMA N axis
 };
 
 template <int STAGES>
@@ -1341,294 +1315,12 @@ __device__ void prefill2_work(const CUtensorMap* qmap, const CUtensorMap* kmap, 
   cta_sync_384();
 }
 
-// ============================================== prefill, 2 row blocks, 64-key tiles (prefill3) ====
-// Same two-block ping-pong as prefill2, but the key tile is 64 rows and every block has TWO S buffers
-// (2 x 64 TMEM columns where prefill2 has one of 128; P_j still in place over the first 32 columns
-// of its buffer), so QK^T of tile j+1 no longer waits for PV of tile j:
-//
-//   prefill2:  softmax_t(j) -> P -> [PV_t(j), QK_t(j+1)] -> S_t(j+1) -> softmax_t(j+1)      a CHAIN
-//   prefill3:  QK_t(j+2) is issued right after PV_t(j) into the buffer P_t(j) vacated, S_t(j+1) is
-//              already there when softmax_t(j) ends: the softmax warpgroups only ever wait for the
-//              tensor pipe when it is the bottleneck, and vice versa.
-// ncu on prefill2 (profiles/r2_prefill2_grid_token_ncu_*): tensor pipe 55 % of active cycles, XU
-// 55 %, and the softmax warps spend 30 % of their stall samples waiting for S -- the chain above, ~3700
-// cycles per 128 keys of a block pair against 2048 of MMA.  Register-resident S needs only 64
-// registers here, so no setmaxnreg.
-constexpr int kBN3 = 64;
-constexpr int kTile3Bytes = kBN3 * kHeadDim * 2;  // 16 KB
-constexpr int kPrefill3Stages = 8;
-constexpr uint32_t kCol3O = 256;  // S_t buffer u at 128 t + 64 u, O_t at 256 + 128 t
-
-struct __align__(1024) Prefill3Smem {
-  uint8_t q[2][kTile * kHeadDim * 2];
-  uint8_t ring[kPrefill3Stages][kTile3Bytes];
-};
-
-__device__ __forceinline__ void load_kv_tile64(uint8_t* dst, const CUtensorMap* full, const CUtensorMap* tail,
-                                               uint64_t* bar, int row0, int head, int slot, int safe_rows,
-                                               int tail_rows) {
-  if (row0 + kBN3 <= safe_rows) {
-    mbar_expect_tx(bar, kTile3Bytes);
-    tma_load_5d(dst, full, bar, 0, row0, 0, head, slot);
-  } else {  // tail_rows < 128 here (a 128-row-safe layout is 64-row-safe), so tail_rows <= 64
-    const int nbox = (safe_rows - row0 + tail_rows - 1) / tail_rows;
-    mbar_expect_tx(bar, nbox * tail_rows * 128 * 2);
-    for (int i = 0; i < nbox; i++)
-      for (int a = 0; a < 2; a++)
-        tma_load_5d(dst + a * (kBN3 * 128) + i * tail_rows * 128, tail, bar, 0, row0 + i * tail_rows, a, head, slot);
-  }
-}
-
-// position in the load / consumption sequence K0 K1 V0 K2 V1 K3 ... of K_j and V_j
-__device__ __forceinline__ int p3_pos_k(int j) { return j < 2 ? j : 2 * j - 1; }
-__device__ __forceinline__ int p3_pos_v(int j, int n) { return seq_pos_v(j, n); }
-
-template <typename T, int ROLE = 0>
-__device__ void prefill3_work(const CUtensorMap* qmap, const CUtensorMap* kmap, const CUtensorMap* vmap,
-                              const CUtensorMap* kmap_tail, const CUtensorMap* vmap_tail,
-                              const PrefillParams& p, Prefill3Smem& sm, TcBarriers& bar, uint32_t tmem,
-                              const PrefillSegment& seg, bool barriers_live) {
-  constexpr int kStages = kPrefill3Stages;
-  constexpr int kBM = kTile, kBN = kBN3, kD = kHeadDim;
-  const int h = seg.h, b = seg.b;
-  const int hkv = h / p.group;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = p.cache_batch_idx ? p.cache_batch_idx[b] : b;
-  const int lk = (p.cache_seqlens ? p.cache_seqlens[b] : p.seqlen_k) + p.seqlen_new;
-  const int shift = lk - p.seqlen_q;
-  // tiles are counted in 64-key units here; seg.j0 / seg.j1 arrive in 128-key units
-  int m0[2], rows[2], nl[2];
-#pragma unroll
-  for (int t = 0; t < 2; t++) {
-    m0[t] = (seg.mt2 * 2 + t) * kBM;
-    rows[t] = min(kBM, p.seqlen_q - m0[t]);
-    int kv_end = lk;
-    if (p.causal) kv_end = min(lk, m0[t] + rows[t] + shift);
-    if (kv_end < 0 || rows[t] <= 0) kv_end = 0;
-    const int nt = (kv_end + kBN - 1) / kBN;
-    const int j1 = seg.j1 >= (1 << 29) ? nt : min(2 * seg.j1, nt);  // (INT_MAX: the whole item)
-    nl[t] = max(0, j1 - 2 * seg.j0);
-  }
-  const int j0 = 2 * seg.j0;
-  const int n = max(nl[0], nl[1]);
-
-  if (threadIdx.x == 0) {
-    mbar_reinit(&bar.q_full, 1, barriers_live);
-    for (int s = 0; s < kStages; s++) {
-      mbar_reinit(&bar.full[s], 1, barriers_live);
-      mbar_reinit(&bar.empty[s], 1, barriers_live);
-    }
-    for (int i = 0; i < 2; i++) {
-      mbar_reinit(&bar.s_full[i], 1, barriers_live);
-      mbar_reinit(&bar.s_full_b[i], 1, barriers_live);
-      mbar_reinit(&bar.p_ready[i], 128, barriers_live);
-      mbar_reinit(&bar.p_ready_b[i], 128, barriers_live);
-      mbar_reinit(&bar.o_full[i], 1, barriers_live);
-      mbar_reinit(&bar.o_full_b[i], 1, barriers_live);
-    }
-    fence_mbar_init();
-  }
-  cta_sync_384();
-
-  if constexpr (ROLE != 2) {
-  if (ROLE == 1 || warp < 4) {
-  if (warp == 0) {
-    // =========================================================== TMA producer ====
-    if (lane == 0 && n > 0) {
-      mbar_expect_tx(&bar.q_full, 2 * kBM * kD * 2);
-      tma_load_5d(sm.q[0], qmap, &bar.q_full, 0, m0[0], 0, h, b);
-      tma_load_5d(sm.q[1], qmap, &bar.q_full, 0, m0[1], 0, h, b);  // rows past seqlen_q arrive as zeros
-      const int safe_rows = (lk + p.tail_rows - 1) / p.tail_rows * p.tail_rows;
-      int pos = 0;
-      auto load = [&](const CUtensorMap* m, const CUtensorMap* mt, int tile) {
-        const int s = pos % kStages;
-        mbar_wait(&bar.empty[s], ((pos / kStages) & 1) ^ 1);
-        load_kv_tile64(sm.ring[s], m, mt, &bar.full[s], (j0 + tile) * kBN, hkv, slot, safe_rows, p.tail_rows);
-        pos++;
-      };
-      load(kmap, kmap_tail, 0);
-      if (n > 1) load(kmap, kmap_tail, 1);
-      for (int j = 0; j < n; j++) {
-        load(vmap, vmap_tail, j);
-        if (j + 2 < n) load(kmap, kmap_tail, j + 2);
-      }
-    }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer ====
-    if (lane == 0 && n > 0) {
-      mbar_wait(&bar.q_full, 0);
-      int pos = 0;
-      auto wait_slot = [&]() {
-        const int s = pos % kStages;
-        mbar_wait(&bar.full[s], (pos / kStages) & 1);
-        tc_fence_after();
-        return s;
-      };
-      auto issue_qk = [&](int t, int j, uint32_t k0) {  // S_t buffer (j & 1) = Q_t . K_j^T
-        const uint32_t q_addr = smem_u32(sm.q[t]);
-#pragma unroll
-        for (int ks = 0; ks < kD / 16; ks++) {
-          const uint32_t qoff = (ks >> 2) * (kBM * 128) + (ks & 3) * 32;
-          const uint32_t koff = (ks >> 2) * (kBN * 128) + (ks & 3) * 32;
-          umma_ss(tmem + t * 128 + (j & 1) * kBN, make_smem_desc(q_addr + qoff, 16, 1024, kLayoutSw128),
-                  make_smem_desc(k0 + koff, 16, 1024, kLayoutSw128), p.idesc_qk64, ks > 0);
-        }
-        umma_commit((j & 1) ? &bar.s_full_b[t] : &bar.s_full[t]);
-      };
-      auto issue_pv = [&](int t, int j, uint32_t v0) {  // O_t += P_t(j) . V_j
-        // Even and odd tiles signal on separate barriers.  A warpgroup may finish tile j+1 before this
-        // thread has looked at tile j (S(j+1) comes from the prologue or from behind PV(j-1)); with one
-        // barrier both phases would complete and the parity wait for tile j would then see an even
-        // number of phases and wait for tile j+2 -- whose S needs PV(j).  Per buffer the producer can
-        // never be two phases ahead: tile j+2 needs QK^T(j+2), issued behind PV(j).
-        mbar_wait((j & 1) ? &bar.p_ready_b[t] : &bar.p_ready[t], (j >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < kBN / 16; ks++)
-          umma_ts(tmem + kCol3O + t * kD, tmem + t * 128 + (j & 1) * kBN + ks * 8,
-                  make_smem_desc(v0 + ks * (16 * 128), kBN * 128, 1024, kLayoutSw128), p.idesc_pv,
-                  (j > 0 || ks > 0) ? 1u : 0u);
-        umma_commit((j & 1) ? &bar.o_full_b[t] : &bar.o_full[t]);  // phase j >> 1 of that barrier
-      };
-      for (int jj = 0; jj < 2 && jj < n; jj++) {  // prologue: S_t(0), S_t(1) into the two buffers
-        const int s = wait_slot();
-        const uint32_t k0 = smem_u32(sm.ring[s]);
-        if (jj < nl[0]) issue_qk(0, jj, k0);
-        if (jj < nl[1]) issue_qk(1, jj, k0);
-        umma_commit(&bar.empty[s]);
-        pos++;
-      }
-      int last_slot = 0;
-      for (int j = 0; j < n; j++) {
-        const int sv = wait_slot();
-        pos++;
-        const uint32_t v0 = smem_u32(sm.ring[sv]);
-        int sk = -1;
-        uint32_t k2 = 0;
-        if (j + 2 < n) {
-          sk = wait_slot();
-          pos++;
-          k2 = smem_u32(sm.ring[sk]);
-        }
-        // per block: PV(j), then QK^T(j+2) into the buffer P(j) leaves (in order behind that PV)
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-          if (j < nl[t]) issue_pv(t, j, v0);
-          if (sk >= 0 && j + 2 < nl[t]) issue_qk(t, j + 2, k2);
-        }
-        umma_commit(&bar.empty[sv]);
-        last_slot = sv;
-        if (sk >= 0) {
-          umma_commit(&bar.empty[sk]);
-          last_slot = sk;
-        }
-      }
-      // drain the last commit (observed by nobody else) before a persistent caller re-initialises
-      const int lp = pos - 1;
-      mbar_wait(&bar.empty[last_slot], (lp / kStages) & 1);
-    }
-  }
-  }
-  }
-  if constexpr (ROLE != 1) {
-  if (ROLE == 2 || warp >= 4) {
-    // ==================================================== softmax / epilogue ====
-    const int t = (warp - 4) >> 2;            // which row block this warpgroup owns
-    const int i = (threadIdx.x - 128) & 127;  // query row inside the block == TMEM lane
-    const int sw = warp & 3;
-    const uint32_t lane_base = (uint32_t)(sw * 32) << 16;
-    const int qi = m0[t] + i;
-    const int my_n = nl[t];
-    int limit = lk - 1;
-    if (p.causal) limit = min(limit, qi + shift);
-    float m_ref = -INFINITY, l = 0.f;
-    const uint32_t o_addr = tmem + lane_base + kCol3O + t * kD;
-
-    for (int j = 0; j < my_n; j++) {
-      mbar_wait((j & 1) ? &bar.s_full_b[t] : &bar.s_full[t], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t s_addr = tmem + lane_base + t * 128 + (j & 1) * kBN;
-      const int key0 = (j0 + j) * kBN;
-      const bool need_mask = key0 + kBN - 1 > limit;
-      const bool warp_mask = __any_sync(0xffffffffu, need_mask);
-      uint32_t s0[32], s1[32];
-      tmem_ld_x32(s_addr, s0);
-      tmem_ld_x32(s_addr + 32, s1);
-      tmem_wait_ld();
-      float mx;
-      if (warp_mask)
-        mx = fmaxf(regs_quarter_max<true>(s0, key0, limit), regs_quarter_max<true>(s1, key0 + 32, limit));
-      else
-        mx = fmaxf(regs_quarter_max<false>(s0, 0, 0), regs_quarter_max<false>(s1, 0, 0));
-      mx *= p.scale_log2;
-      float alpha = 1.f;
-      bool grow = mx > m_ref + kRescaleThreshold;
-      if (m_ref == -INFINITY && mx > -INFINITY) grow = true;
-      if (grow) {
-        alpha = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - mx);
-        m_ref = mx;
-      }
-      if (__any_sync(0xffffffffu, grow) && j > 0) {
-        // O must hold every earlier tile before it is rescaled: S_t(j) only proves PV_t(j-2) retired.
-        // (PV_t(j-3) is known complete -- S_t(j-1) was ready -- so the barrier of tile j-1's parity is
-        // at most one phase behind: the wait is unambiguous)
-        mbar_wait(((j - 1) & 1) ? &bar.o_full_b[t] : &bar.o_full[t], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < kD; c += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(o_addr + c, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; e++) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-          tmem_st_x32(o_addr + c, r);
-        }
-        tmem_wait_st();
-      }
-      l *= alpha;
-      const float mref_safe = (m_ref == -INFINITY) ? 0.f : m_ref;
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t packed[32];
-      if (warp_mask) {
-        regs_quarter_exp<T, true>(s0, packed, p.scale_log2, mref_safe, key0, limit, ls);
-        regs_quarter_exp<T, true>(s1, packed + 16, p.scale_log2, mref_safe, key0 + 32, limit, ls);
-      } else {
-        regs_quarter_exp<T, false>(s0, packed, p.scale_log2, mref_safe, 0, 0, ls);
-        regs_quarter_exp<T, false>(s1, packed + 16, p.scale_log2, mref_safe, 0, 0, ls);
-      }
-      tmem_st_x32(s_addr, packed);  // P_t(j): 64 keys, 2 per column, over the consumed half of its S buffer
-      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      tmem_wait_st();
-      if ((j0 + j + 1) * kBN > lk) {
-        const int pv = p3_pos_v(j, n);
-        mbar_wait(&bar.full[pv % kStages], (pv / kStages) & 1);
-        // both warpgroups may reach the tail tile: zeroing the same rows twice is harmless
-        if (i < kBN && key0 + i >= lk) {
-          uint8_t* vt = sm.ring[pv % kStages];
-#pragma unroll
-          for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int c = 0; c < 8; c++)
-              *reinterpret_cast<uint4*>(vt + a * (kBN * 128) + i * 128 + c * 16) = make_uint4(0, 0, 0, 0);
-        }
-        fence_proxy_async_smem();
-      }
-      tc_fence_before();
-      mbar_arrive((j & 1) ? &bar.p_ready_b[t] : &bar.p_ready[t]);
-    }
-
-    if (my_n > 0) {
-      // the last two PVs, one on each barrier (each is at most one phase behind, see above)
-      if (my_n > 1) mbar_wait(((my_n - 2) & 1) ? &bar.o_full_b[t] : &bar.o_full[t], ((my_n - 2) >> 1) & 1);
-      mbar_wait(((my_n - 1) & 1) ? &bar.o_full_b[t] : &bar.o_full[t], ((my_n - 1) >> 1) & 1);
-      tc_fence_after();
-    }
-    prefill_block_epilogue<T>(p, seg, bar, tmem, o_addr, t, i, qi, h, b, rows[t], my_n, m_ref, l);
-  }
-  }
-  tc_fence_before();
-  cta_sync_384();
-}
+// (A variant with 64-key tiles and TWO S buffers per row block -- QK^T of tile j+2 issued right behind
+// PV of tile j, so that S(j+1) is already there when the softmax of tile j ends -- was built, parity
+// tested and measured in round 2: 765 / 635 / 806 TFLOP/s at chunk 2048 / 512 / 8192 against 975 / 788 /
+// 1057 for prefill2; ncu: tensor pipe 37 %, XU 37 %, softmax warps waiting for S 40 % of their samples
+// (profiles/r2_prefill3_discarded_ncu_*).  One tile of look-ahead at half the tile size does not cover
+// the ~500-cycle round trip P -> MMA thread -> tensor pipe -> commit -> softmax; removed.)
 
 }  // namespace tcwork
 }  // namespace vattn
