@@ -292,12 +292,16 @@ def run_ours(args):
         va.step_async(slot_lens)                  # pages for this token are mapped on return
         return new
 
+    # graph replays need static shapes: the views end at a bound no sequence reaches during the run
+    # (the wrapper's per-step slice [:, :max_cache_len], vattention_flashattention_wrapper.py:197, with
+    # the maximum taken over the whole run)
+    static_len = min(max_ctx, max(seq_lens) + total_steps + 8)
+
     def layers_body(full_views: bool, max_len: int = 0):
         out = None
         for layer in range(LAYERS):
             kc, vc = k_layers[layer % n_res], v_layers[layer % n_res]
-            if not full_views:
-                kc, vc = kc[:, :max_len], vc[:, :max_len]
+            kc, vc = (kc[:, :static_len], vc[:, :static_len]) if full_views else (kc[:, :max_len], vc[:, :max_len])
             out = tp_attn.forward(q[layer], kc, vc, kn[layer], vn[layer], cache_seqlens=cs,
                                   cache_batch_idx=batch_idx, softmax_scale=scale, causal=True)
         sink.add_(out.flatten()[0].float())

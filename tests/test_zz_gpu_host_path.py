@@ -2,11 +2,9 @@
 
 vattn_fwd_kvcache_host / _host_async take q, k_new, v_new, cache_seqlens, cache_batch_idx and out in HOST
 memory, the caches on the device.  (File name sorts last on purpose: these entry points were exercised by
-the bench long before they had a parity test.)  The pipelined variant is opt-in until it has been measured:
-VATTN_TEST_PIPELINED=1 enables its case.
+the bench long before they had a parity test.)  The pipelined variant (copies on their own streams) is what the
+bench's e2e leg uses: measured 1679 vs 1606 tokens/s for the in-line copies.
 """
-import os
-
 import pytest
 import torch
 
@@ -53,7 +51,6 @@ def test_host_buffers_match_oracle(wait):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.skipif(os.environ.get("VATTN_TEST_PIPELINED") != "1", reason="opt-in: VATTN_TEST_PIPELINED=1")
 def test_pipelined_host_calls_match_oracle():
     """Eight back-to-back pipelined calls with different inputs (both staging slots reused several times),
     one join, one synchronise; every output and the final cache state must match."""
