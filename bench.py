@@ -212,10 +212,13 @@ def run_ours(args):
     # every step of the run, in order: graph warm-up (2) + W + K timed + K eager (kernel timing) +
     # e2e (W + K) + parity (1)
     total_steps = 3 + W + K + K + (0 if args.no_e2e else W + K) + 2
-    # sequence b starts (b mod spread) + 1 tokens below the boundary: one or two sequences cross into
-    # the next page at every step of the run; mean length over the timed region ~= CTX
-    spread = max(8, min(total_steps, 2 * (W + K)))
-    seq_lens = [CTX - (b % spread) - 1 - (W + 2) for b in range(B)]
+    # sequence b starts off_b + 1 tokens below the boundary, off_b spread evenly over `spread` tokens, so
+    # sequences cross into the next page one after another during the run.  `spread` is a fixed
+    # FRACTION of this rank's page (tokens per page grow with N as the kv heads are sharded), i.e. page
+    # crossings come ~45x more often than with uniformly distributed lengths at every N -- the same
+    # token stream maps the same BYTES per step on every rank count, not N times more.
+    spread = max(8, min(total_steps, 2 * (W + K))) * (tpp // (PAGE // (wl.hkv * D * 2)))
+    seq_lens = [CTX - (b * spread) // B - 1 - (W + 2) for b in range(B)]
     torch.zeros(1, device=dev)                  # context for the allocator (cudaInternal.h:19-25)
     n_res = args.resident_layers
     max_ctx = CTX + tpp                          # one page of head-room past the boundary
@@ -489,7 +492,8 @@ def run_ours(args):
             "ms_per_step": round(ms / K, 3), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": f"synthetic N(0,1) q/k/v, lengths straddling the {CTX // 1024}K page boundary "
-                    f"(mean {total_len_first / B + K / 2:.0f}), shuffled cache_batch_idx",
+                    f"(mean {total_len_first / B + K / 2:.0f}, crossings spread over {spread} tokens = 1/{tpp // spread} of a "
+                    f"page), shuffled cache_batch_idx",
             "config": {"workload": wl.name,
                        "shapes": f"B{B} Hq{wl.hq} Hkv{wl.hkv} D{D} L{LAYERS} ctx{CTX} hidden{HIDDEN}",
                        "backend": "fa_vattn_2mb (vAttention virtual tensors, 2 MiB pages, step_async)",
@@ -528,9 +532,10 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of decode_tc_kernel on the decode32k
 # shapes, from an `ncu --set full` capture -- not a measurement of this run (profiles/README.md)
-TRAFFIC_CAPTURE = {"bytes": 8610037000,
-                   "source": "ncu --set full capture of one launch, profiles/r1_decode_tc_ncu_raw.csv "
-                             "(uniform 32K lengths; 1.0025 x algorithmic)"}
+TRAFFIC_CAPTURE = {"bytes": 8610056664,
+                   "source": "ncu --set full capture of one launch of this command's decode_tc_kernel, "
+                             "profiles/r2_decode_tc_headline_ncu_raw.csv (dram read 8.590103 GB + write "
+                             "19.95 MB; 1.002 x algorithmic; lengths straddling the page boundary)"}
 
 
 def parity_check(att, dist, dev, rank, world, wl, shard, tp_attn, w_o, q0, kn0, vn0, kc, vc, cs, batch_idx,
