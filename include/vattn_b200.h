@@ -127,13 +127,25 @@ int vattn_wait_background(vattn_allocator_t* a);
  * so a page is never pulled from under an in-flight kernel.  enable = 0 turns
  * the fence off (stream NULL with enable = 1 means the legacy default stream). */
 int vattn_set_compute_stream(vattn_allocator_t* a, void* stream, int enable);
-/* Timing of the last step / background pass, nanoseconds (host clock).      */
+/* step_async may be QUEUED behind the mapper pass still in flight instead of waiting for it, when
+ * the new lengths need no page beyond those every request already held when that pass started and
+ * the pass cannot take pages back: the mapper then runs exactly the operations the reference runs
+ * (pass, prepare = no-op, pass) while the caller goes on launching kernels.  on = 0 restores the
+ * reference's wait at the top of every step_async (utils.h:160-164).  Default: on.              */
+int vattn_set_queueing(vattn_allocator_t* a, int on);
+/* Timing of the last step / background pass, nanoseconds (host clock), and totals since
+ * init_kvcache.  The call waits for the mapper to be idle (like every call but step_async): a loop
+ * that must not stand still reads the totals once at its end.                                   */
 typedef struct {
   uint64_t critical_path_ns;   /* time inside the last step / step_async call  */
   uint64_t background_ns;      /* duration of the last mapper-thread pass      */
   uint64_t sync_pages_mapped;  /* pages (not blocks) mapped on the critical path */
   uint64_t async_pages_mapped; /* pages mapped by the last background pass     */
   uint64_t driver_calls;       /* cumulative driver VMM calls                  */
+  uint64_t total_critical_path_ns, total_background_ns, max_background_ns;
+  uint64_t total_sync_pages, total_async_pages;
+  uint64_t steps, passes;      /* step / step_async calls; mapper passes       */
+  uint64_t queued_steps;       /* step_async calls that rode behind a pass     */
 } vattn_step_stats_t;
 int vattn_get_step_stats(vattn_allocator_t* a, vattn_step_stats_t* out);
 
@@ -153,6 +165,11 @@ void vattn_clear_driver_log(vattn_allocator_t* a);
 /* HOST_MOCK only: the mock driver's "device" holds `bytes` of physical memory: a create that
  * would exceed it fails like cuMemCreate does when the device is full (0 = unlimited).       */
 void vattn_mock_set_capacity(vattn_allocator_t* a, uint64_t bytes);
+/* HOST_MOCK only: every map / set_access / unmap of the mock driver takes `us` microseconds (a slow
+ * driver: several processes mapping at once), so host tests can show what the caller waits for.  */
+void vattn_mock_set_call_delay_us(vattn_allocator_t* a, uint64_t us);
+/* HOST_MOCK only: fence records / host waits seen by the mock driver, per slot {rec0, rec1, wait0, wait1} */
+void vattn_mock_fence_counts(vattn_allocator_t* a, uint64_t out[4]);
 
 /* ------------------------------------------------------------------------ */
 /* Part B: attention over the contiguous K/V                                 */

@@ -434,3 +434,152 @@ def test_grow_rolls_back_when_the_driver_fails_mid_block(mock_backend):
     va.step([1, 1], True)                            # and the same step succeeds afterwards
     assert va.get_state()["mapped_pages"] == [1, 1]
     assert len(va.get_state()["pool"]) == n - 2 * 2 * L
+
+
+# ---- step_async queued behind a mapper pass that is still in flight ------------------------------
+
+def _decode_steps(model, lens, steps, ctx, read_state_every=0):
+    """`steps` decode iterations back to back: no call that waits for the mapper in between."""
+    import time
+    took = []
+    for s in range(steps):
+        lens = [min(n + 1, ctx - 1) if n else 0 for n in lens]
+        t0 = time.perf_counter()
+        va.step_async(lens)
+        took.append(time.perf_counter() - t0)
+        model.step_async(lens)
+        if read_state_every and (s + 1) % read_state_every == 0:
+            assert_same(model)
+    return lens, took
+
+
+def test_step_async_rides_behind_a_slow_pass(mock_backend):
+    """A slow driver (5 ms per map / set_access) makes the eager pass take tens of milliseconds.  The
+    next decode steps need no new page, so they are queued behind it and return at once; the
+    bookkeeping ends up exactly where the oracle's strictly sequential replay ends up."""
+    model, _ = make_pair(2, 2, 64, 4, 32768, mem_pages=64)
+    tpp = model.tokens_per_page
+    lens = [tpp - 9, tpp - 30, 100, 5000]            # the first pass looks 9 tokens ahead: no new page yet
+    va.step_async(lens)
+    model.step_async(lens)
+    va.wait_background()
+    va.mock_set_call_delay_us(5000)
+    lens, took = _decode_steps(model, lens, 3, 32768)
+    st = va.get_step_stats()                         # waits for the mapper
+    # pass of step 1 maps request 0's next page in both layers (4 maps + 4 set_access = 40 ms); the
+    # two steps after it rode behind
+    assert st["queued_steps"] >= 1
+    assert st["max_background_ns"] > 30e6
+    assert min(took[1:]) < 0.010, took
+    assert st["total_sync_pages"] == 2 * 2 * 4       # only the very first step mapped on the critical path
+    assert_same(model)
+    va.mock_set_call_delay_us(0)
+    lens, _ = _decode_steps(model, lens, 40, 32768, read_state_every=7)   # across the boundary
+    assert_same(model)
+    assert va.get_state()["mapped_pages"][0] == 2
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("nodefer", [False, True])
+def test_queued_steps_match_oracle_on_random_traces(mock_backend, seed, nodefer):
+    """Random serving traces with a slow driver and NO state reads between decode steps: whichever
+    steps happen to be queued, mapped_pages / pool order / page map / driver calls equal the oracle's."""
+    L, Hkv, D, B, ctx = 2, 2, 64, 5, 32768
+    model, _ = make_pair(L, Hkv, D, B, ctx, mem_pages=200)
+    if nodefer:
+        va.set_deferred_reclamation(False)
+        model.set_deferred_reclamation(False)
+    tpp = model.tokens_per_page
+    rng = random.Random(500 + seed)
+    va.mock_set_call_delay_us(150)
+    lens = [0] * B
+    for it in range(60):
+        r = rng.random()
+        active = [i for i in range(B) if lens[i]]
+        if r < 0.3 and len(active) < B:
+            n = rng.choice([1, tpp - 2, tpp, tpp + 1, 2 * tpp - 3, rng.randrange(1, ctx // 3)])
+            got, want = va.alloc_new_batch_idx(n), model.alloc_new_batch_idx(n)
+            assert got == want
+            if got >= 0:
+                lens[got] = n
+        elif r < 0.4 and active:
+            i = rng.choice(active)
+            va.free_batch_idx(i)
+            model.free_batch_idx(i)
+            lens[i] = 0
+        try:
+            lens, _ = _decode_steps(model, lens, rng.randrange(1, 6), ctx)
+        except (RuntimeError, AllocatorOOM):
+            pytest.skip("trace ran out of pages")   # (sized not to; OOM parity is covered above)
+    assert_same(model)
+    st = va.get_step_stats()
+    assert st["steps"] > 60
+    # ... and the driver saw the maps / unmaps in the reference's order with the reference's pages
+    log = va.get_driver_log()
+    reserves = [r for r in log if r[0] == 1]
+    base = {f"k{i}": reserves[i][1] for i in range(L)}
+    base.update({f"v{i}": reserves[L + i][1] for i in range(L)})
+    got = [(r[0], r[1], r[3] - 1 if r[0] == 3 else -1) for r in log if r[0] in (3, 5)]
+    want = [(3 if c.op == "map" else 5, base[c.tensor] + c.offset, c.page if c.op == "map" else -1)
+            for c in model.calls if c.op in ("map", "unmap")]
+    assert got == want
+
+
+def test_queueing_is_refused_when_the_pass_takes_pages_back(mock_backend):
+    """With the pool empty the background pass takes an inactive request's page back
+    (reclaim_on_demand) to map the page request 0 needs next: no step may be queued behind THAT pass,
+    the call waits like the reference does.  Either way the books equal the oracle's."""
+    model, _ = make_pair(1, 2, 64, 3, 32768, mem_pages=2 * 3)   # three blocks in all
+    tpp = model.tokens_per_page
+    lens = [tpp - 5, 10, 10]
+    va.step_async(lens)
+    model.step_async(lens)
+    va.free_batch_idx(2)                                         # keeps its page (deferred reclamation)
+    model.free_batch_idx(2)
+    lens[2] = 0
+    assert_same(model)
+    va.mock_set_call_delay_us(2000)
+    lens, _ = _decode_steps(model, lens, 9, 32768)               # request 0 crosses the boundary
+    assert_same(model)
+    st = va.get_state()
+    assert st["mapped_pages"] == [2, 1, 0]                       # the page moved from request 2 to request 0
+    assert va.get_step_stats()["queued_steps"] < 9
+    va.mock_set_call_delay_us(0)
+
+
+def test_set_queueing_off_waits_like_the_reference(mock_backend):
+    model, _ = make_pair(2, 2, 64, 4, 32768, mem_pages=64)
+    tpp = model.tokens_per_page
+    va.set_queueing(False)
+    lens = [tpp - 9, tpp - 30, 100, 5000]
+    va.step_async(lens)
+    model.step_async(lens)
+    va.wait_background()
+    va.mock_set_call_delay_us(3000)
+    lens, took = _decode_steps(model, lens, 3, 32768)
+    assert va.get_step_stats()["queued_steps"] == 0
+    assert took[1] > 0.015                           # stood still for the pass of the step before
+    assert_same(model)
+    va.mock_set_call_delay_us(0)
+
+
+def test_queued_step_records_its_fence_in_the_other_slot(mock_backend):
+    """Unmaps wait for an event recorded on the compute stream at THEIR step's step_async.  A queued
+    step records into the slot the pass in flight is not using; the mapper switches slots when it
+    takes the step on."""
+    model, _ = make_pair(1, 2, 64, 3, 32768, mem_pages=12)
+    tpp = model.tokens_per_page
+    va.set_compute_stream(0, True)
+    lens = [tpp - 9, 7, 0]
+    va.step_async(lens)
+    model.step_async(lens)
+    va.wait_background()
+    va.mock_set_call_delay_us(4000)
+    lens, _ = _decode_steps(model, lens, 3, 32768)
+    st = va.get_step_stats()
+    fc = va.mock_fence_counts()
+    assert sum(fc["records"]) == st["steps"]
+    if st["queued_steps"]:
+        assert fc["records"][0] and fc["records"][1]
+    assert_same(model)
+    va.mock_set_call_delay_us(0)

@@ -30,7 +30,8 @@ class VattnConfig(C.Structure):
 class StepStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "critical_path_ns", "background_ns", "sync_pages_mapped", "async_pages_mapped",
-        "driver_calls")]
+        "driver_calls", "total_critical_path_ns", "total_background_ns", "max_background_ns",
+        "total_sync_pages", "total_async_pages", "steps", "passes", "queued_steps")]
 
 
 class FwdParams(C.Structure):
@@ -104,6 +105,9 @@ _SIGS = {
     "vattn_get_driver_log": (C.c_size_t, [_A, _P(C.c_uint64), C.c_size_t]),
     "vattn_clear_driver_log": (None, [_A]),
     "vattn_mock_set_capacity": (None, [_A, C.c_uint64]),
+    "vattn_mock_set_call_delay_us": (None, [_A, C.c_uint64]),
+    "vattn_mock_fence_counts": (None, [_A, C.POINTER(C.c_uint64)]),
+    "vattn_set_queueing": (C.c_int, [_A, C.c_int]),
     "vattn_fwd_kvcache_workspace": (C.c_size_t, [_P(FwdParams)]),
     "vattn_fwd_kvcache": (C.c_int, [_P(FwdParams), C.c_void_p]),
     "vattn_single_prefill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64,

@@ -275,6 +275,22 @@ int vattn_get_step_stats(vattn_allocator_t* a, vattn_step_stats_t* out) {
   out->sync_pages_mapped = s.sync_pages_mapped;
   out->async_pages_mapped = s.async_pages_mapped;
   out->driver_calls = a->impl->driver()->calls();
+  out->total_critical_path_ns = s.total_critical_path_ns;
+  out->total_background_ns = s.total_background_ns;
+  out->max_background_ns = s.max_background_ns;
+  out->total_sync_pages = s.total_sync_pages;
+  out->total_async_pages = s.total_async_pages;
+  out->steps = s.steps;
+  out->passes = s.passes;
+  out->queued_steps = s.queued_steps;
+  return VATTN_OK;
+  VATTN_CATCH
+}
+
+int vattn_set_queueing(vattn_allocator_t* a, int on) {
+  if (!check_handle(a)) return VATTN_ERR_INVALID;
+  VATTN_TRY
+  a->impl->set_queueing(on != 0);
   return VATTN_OK;
   VATTN_CATCH
 }
@@ -331,6 +347,17 @@ void vattn_mock_set_capacity(vattn_allocator_t* a, uint64_t bytes) {
     a->impl->wait_background();
     a->mock->set_capacity(bytes);
   }
+}
+
+void vattn_mock_set_call_delay_us(vattn_allocator_t* a, uint64_t us) {
+  if (check_handle(a) && a->mock) a->mock->set_call_delay_us(us);
+}
+
+void vattn_mock_fence_counts(vattn_allocator_t* a, uint64_t out[4]) {
+  if (!check_handle(a) || !a->mock || !out) return;
+  a->impl->wait_background();
+  out[0] = a->mock->fence_records(0), out[1] = a->mock->fence_records(1);
+  out[2] = a->mock->fence_waits(0), out[3] = a->mock->fence_waits(1);
 }
 
 void vattn_clear_driver_log(vattn_allocator_t* a) {

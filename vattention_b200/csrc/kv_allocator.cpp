@@ -132,6 +132,8 @@ std::vector<u64> KvAllocator::init_kvcache(u64 num_layers, u64 num_kv_heads, u64
   pagemap_.clear();
   shared_refs_.clear();
   chunks_.clear();
+  stats_ = StepStats{};
+  queued_ = false;
   configured_ = true;
   log("Initialized CUDA context and memory config etc...");
   log("num_tokens_per_kvblock: " + std::to_string(c.tokens_per_page));
@@ -349,7 +351,7 @@ void KvAllocator::unmap_one(u64 req) {
   if (mapped_pages_[req] == 0) throw StateError("[vattn] unmap on a request with no pages");
   const u64 nl = cfg_.megacache ? 1 : cfg_.num_layers;
   const u64 off = req * cfg_.per_req + (mapped_pages_[req] - 1) * cfg_.page_size;  // utils.h:193-204
-  if (fence_enabled_) drv_->wait_fence();
+  if (fence_enabled_) drv_->wait_fence(fence_slot_);
   for (u64 layer = 0; layer < nl; layer++) {
     auto it = pagemap_.find(Key(req, off, layer));
     if (it == pagemap_.end()) throw StateError("[vattn] page map entry missing on unmap");
@@ -428,6 +430,14 @@ u64 KvAllocator::need_new_page_async(u64 req, u64 eager) const {
   return need <= have ? 0 : need - have;
 }
 
+bool KvAllocator::pass_will_reclaim() const {
+  // the first decision of background_pass, taken from the same state (nothing changes between the
+  // hand-off and the pass)
+  u64 nr_required = 0;
+  for (u64 r = 0; r < cfg_.max_batch_size; r++) nr_required += need_new_page_async(r, 1);
+  return !kvblocks_available(nr_required);
+}
+
 void KvAllocator::background_pass() {
   // vattention.cu:488-536
   u64 nr_required = 0;
@@ -464,22 +474,44 @@ void KvAllocator::mapper_main() {
     cv_.wait(lk, [&] { return job_pending_ || stop_; });
     if (stop_) return;
     job_pending_ = false;
-    // busy_ was set by step_async under the lock, so no API call can slip in
-    // between the hand-off and this pass (reference hazard (a)).
-    u64 t0 = now_ns();
-    try {
-      if (!bound) {
-        drv_->bind_thread();
-        bound = true;
+    // busy_ was set by step_async under the lock, so no API call can slip in between the hand-off
+    // and this pass (reference hazard (a)).  While busy_ is set this thread owns the
+    // bookkeeping; mu_ is released so that step_async can look at the hand-off snapshot and queue
+    // the next step instead of standing still for the whole pass.
+    for (;;) {
+      lk.unlock();
+      const u64 t0 = now_ns();
+      std::string err;
+      try {
+        if (!bound) {
+          drv_->bind_thread();
+          bound = true;
+        }
+        stats_.async_pages_mapped = 0;
+        background_pass();
+      } catch (const std::exception& e) {
+        err = e.what();
       }
-      stats_.async_pages_mapped = 0;
-      // the pass runs with mu_ held: every API entry waits on !busy_ anyway,
-      // holding the lock just makes that explicit.
-      background_pass();
-    } catch (const std::exception& e) {
-      bg_error_ = e.what();
+      const u64 dt = now_ns() - t0;
+      lk.lock();
+      stats_.background_ns = dt;
+      stats_.total_background_ns += dt;
+      stats_.total_async_pages += stats_.async_pages_mapped;
+      if (dt > stats_.max_background_ns) stats_.max_background_ns = dt;
+      stats_.passes++;
+      if (!err.empty()) bg_error_ = err;
+      if (!queued_ || !bg_error_.empty()) break;
+      // the queued step: what step_async does after its wait -- the lengths are replaced, preparing
+      // the step maps nothing (that is what let it queue), the next pass starts
+      queued_ = false;
+      seq_lens_ = queued_lens_;
+      fence_slot_ ^= 1;  // the queued step recorded its fence in the other slot
+      handoff_lens_ = seq_lens_;
+      handoff_mapped_ = mapped_pages_;
+      handoff_reclaims_ = pass_will_reclaim();
+      cv_.notify_all();  // a step_async waiting for the queue slot
     }
-    stats_.background_ns = now_ns() - t0;
+    queued_ = false;  // (only after an error: the queued lengths are dropped with it)
     busy_ = false;
     cv_.notify_all();
   }
@@ -493,7 +525,7 @@ void KvAllocator::step_sync(const u64* seq_lens, size_t n, bool eager_reclaim) {
   wait_idle(lk);
   require_configured();
   if (n != cfg_.max_batch_size) throw InvalidError("[vattn] seq_lens must have max_batch_size entries");
-  if (fence_enabled_) drv_->record_fence(compute_stream_);
+  if (fence_enabled_) drv_->record_fence(compute_stream_, fence_slot_);
   stats_.sync_pages_mapped = 0;
   // vattention.cu:395-409
   for (u64 r = 0; r < cfg_.max_batch_size; r++) {
@@ -505,25 +537,68 @@ void KvAllocator::step_sync(const u64* seq_lens, size_t n, bool eager_reclaim) {
     map_for_curr_step(r, seq_lens[r], &stats_.sync_pages_mapped);
   }
   stats_.critical_path_ns = now_ns() - t0;
+  stats_.total_critical_path_ns += stats_.critical_path_ns;
+  stats_.total_sync_pages += stats_.sync_pages_mapped;
+  stats_.steps++;
+}
+
+void KvAllocator::hand_off_locked() {
+  // spawn_kvcache_manager, vattention.cu:538-546 -> wake the parked mapper
+  handoff_lens_ = seq_lens_;
+  handoff_mapped_ = mapped_pages_;
+  handoff_reclaims_ = pass_will_reclaim();
+  busy_ = true;
+  job_pending_ = true;
+}
+
+bool KvAllocator::can_ride_behind(const u64* seq_lens, size_t n) const {
+  // The pass in flight started from handoff_lens_ / handoff_mapped_.  Unless it takes pages back
+  // (handoff_reclaims_), it only ADDS pages to requests that were active at the hand-off and only
+  // removes pages from requests that were not.  So if every request of the new step was active then
+  // and already had the pages the new length needs, preparing this step would map nothing whenever
+  // it ran: it can be queued behind the pass.
+  if (handoff_reclaims_) return false;
+  for (size_t r = 0; r < n; r++) {
+    if (seq_lens[r] == 0) continue;
+    if (handoff_lens_[r] == 0) return false;
+    if (tokens_to_pages(seq_lens[r]) > handoff_mapped_[r]) return false;
+  }
+  return true;
 }
 
 void KvAllocator::step_async(const u64* seq_lens, size_t n) {
   u64 t0 = now_ns();
   std::unique_lock<std::mutex> lk(mu_);
+  if (busy_ && queueing_ && configured_ && n == cfg_.max_batch_size && bg_error_.empty()) {
+    // at most one step rides behind the pass in flight
+    cv_.wait(lk, [&] { return !busy_ || !queued_; });
+    if (busy_ && bg_error_.empty() && can_ride_behind(seq_lens, n)) {
+      queued_lens_.assign(seq_lens, seq_lens + n);
+      queued_ = true;
+      if (fence_enabled_) drv_->record_fence(compute_stream_, fence_slot_ ^ 1);
+      stats_.sync_pages_mapped = 0;
+      stats_.critical_path_ns = now_ns() - t0;
+      stats_.total_critical_path_ns += stats_.critical_path_ns;
+      stats_.steps++;
+      stats_.queued_steps++;
+      return;
+    }
+  }
   // vattention.cu:549-558, with the wait moved BEFORE the lengths are replaced
   // (reference hazard (b)): the previous pass must not see the new lengths.
   wait_idle(lk);
   require_configured();
   if (n != cfg_.max_batch_size) throw InvalidError("[vattn] seq_lens must have max_batch_size entries");
-  if (fence_enabled_) drv_->record_fence(compute_stream_);
+  if (fence_enabled_) drv_->record_fence(compute_stream_, fence_slot_);
   seq_lens_.assign(seq_lens, seq_lens + n);
   stats_.sync_pages_mapped = 0;
   // prepare_prefill_kvcache, vattention.cu:412-418
   for (u64 r = 0; r < cfg_.max_batch_size; r++) map_for_curr_step(r, seq_lens_[r], &stats_.sync_pages_mapped);
-  // spawn_kvcache_manager, vattention.cu:538-546 -> wake the parked mapper
-  busy_ = true;
-  job_pending_ = true;
+  hand_off_locked();
   stats_.critical_path_ns = now_ns() - t0;
+  stats_.total_critical_path_ns += stats_.critical_path_ns;
+  stats_.total_sync_pages += stats_.sync_pages_mapped;
+  stats_.steps++;
   lk.unlock();
   cv_.notify_all();
 }
@@ -684,6 +759,12 @@ void KvAllocator::set_compute_stream(void* stream, bool enable) {
   wait_idle(lk);
   compute_stream_ = stream;
   fence_enabled_ = enable;
+}
+
+void KvAllocator::set_queueing(bool on) {
+  std::unique_lock<std::mutex> lk(mu_);
+  wait_idle(lk);
+  queueing_ = on;
 }
 
 StepStats KvAllocator::stats() {

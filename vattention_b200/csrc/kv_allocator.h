@@ -9,9 +9,16 @@
 //   * one persistent mapper thread parked on a condition variable instead of a
 //     detached std::thread per step (vattention.cu:538-546); the context is made
 //     current on it once;
-//   * state lives in an object guarded by a mutex, not file-scope globals
-//     (utils.h:12-81); every API call first waits for the mapper to be idle, so
-//     none of the reference's racy reads (SURVEY 5 hazards a-c) exist;
+//   * state lives in an object, not file-scope globals (utils.h:12-81); while a pass is
+//     in flight the mapper thread owns the bookkeeping and every API call first waits
+//     for it to be idle, so none of the reference's racy reads (SURVEY 5 hazards a-c)
+//     exist.  One exception, step_async itself: when the lengths of the next step need
+//     no page the in-flight pass has not already been seen to hold (and that pass
+//     cannot take pages back), the step is QUEUED behind the pass instead of waiting
+//     for it -- the mapper runs the same operations in the same order the reference
+//     would (pass, no-op prepare, pass), only the caller does not stand still
+//     meanwhile.  A slow driver (eight processes mapping at once) then costs nothing
+//     on the critical path as long as eager mapping stays one page ahead;
 //   * cuMemSetAccess is issued once per contiguous range per tensor instead of
 //     once per page (cudaInternal.h:77-80);
 //   * cuMemUnmap is fenced behind an event recorded on the compute stream;
@@ -56,8 +63,12 @@ struct KvConfig {
 };
 
 struct StepStats {
-  u64 critical_path_ns = 0, background_ns = 0;
+  u64 critical_path_ns = 0, background_ns = 0;      // last step call / last background pass
   u64 sync_pages_mapped = 0, async_pages_mapped = 0;
+  // since init_kvcache (a caller that does not want to wait for the mapper every step reads these once)
+  u64 total_critical_path_ns = 0, total_background_ns = 0;
+  u64 total_sync_pages = 0, total_async_pages = 0;
+  u64 max_background_ns = 0, steps = 0, passes = 0, queued_steps = 0;
 };
 
 struct PhysPage {
@@ -88,6 +99,7 @@ class KvAllocator {
 
   void wait_background();
   void set_compute_stream(void* stream, bool enable);
+  void set_queueing(bool on);  // step_async may ride behind an in-flight pass (default on)
   StepStats stats();
   KvConfig config();
   void get_state(u64* mapped, u64* lens, size_t n);
@@ -98,7 +110,8 @@ class KvAllocator {
  private:
   using Key = std::tuple<u64, u64, u64>;  // (reqId, req_offset, layer)  utils.h:24
 
-  // ---- policy (all called with mu_ held, mapper idle or being the mapper) ----
+  // ---- policy (called by an API thread with mu_ held and the mapper idle, or by the mapper thread
+  // during its pass: busy_ hands it the bookkeeping, so it runs WITHOUT mu_) ----
   u64 tokens_to_pages(u64 t) const { return (t + cfg_.tokens_per_page - 1) / cfg_.tokens_per_page; }
   u64 blocks_in_pool() const;
   bool kvblocks_available(u64 n) const { return blocks_in_pool() >= n; }
@@ -115,7 +128,10 @@ class KvAllocator {
   void reclaim_on_demand(u64 nblocks);
   void do_reclaim_pages();
   u64 need_new_page_async(u64 req, u64 eager) const;
+  bool pass_will_reclaim() const;
   void background_pass();
+  void hand_off_locked();                                    // snapshot + wake the mapper
+  bool can_ride_behind(const u64* seq_lens, size_t n) const;  // see step_async
   void dump_state_locked();
   void log(const std::string& s) const;
   void require_configured() const;
@@ -143,7 +159,16 @@ class KvAllocator {
 
   void* compute_stream_ = nullptr;
   bool fence_enabled_ = false;
+  int fence_slot_ = 0;  // the driver fence slot of the step the mapper is (or was last) working on
   StepStats stats_;
+
+  // what the in-flight pass started from (written under mu_ at hand-off, read under mu_): lower
+  // bounds an API thread may rely on while the mapper owns the live bookkeeping
+  std::vector<u64> handoff_lens_, handoff_mapped_;
+  bool handoff_reclaims_ = false;  // that pass takes pages back (reclaim_on_demand)
+  bool queueing_ = true;
+  bool queued_ = false;            // one step rides behind the in-flight pass
+  std::vector<u64> queued_lens_;
 
   std::mutex mu_;
   std::condition_variable cv_;

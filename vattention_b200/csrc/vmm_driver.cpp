@@ -6,14 +6,19 @@
 #include <cuda.h>
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 namespace vattn {
 
 // ------------------------------------------------------------------ mock ---
 
 void MockVmmDriver::log(u64 op, u64 va, u64 size, u64 h) {
+  const u64 us = delay_us_.load(std::memory_order_relaxed);
+  if (us && (op == OP_MAP || op == OP_SET_ACCESS || op == OP_UNMAP))
+    std::this_thread::sleep_for(std::chrono::microseconds(us));
   std::lock_guard<std::mutex> g(mu_);
   ++calls_;
   log_.push_back({op, va, size, h});
@@ -130,7 +135,8 @@ class CudaVmmDriver : public VmmDriver {
   }
 
   ~CudaVmmDriver() override {
-    if (fence_) cuEventDestroy_(fence_);
+    for (CUevent e : fence_)
+      if (e) cuEventDestroy_(e);
   }
 
   u64 init(int device) override {
@@ -192,15 +198,19 @@ class CudaVmmDriver : public VmmDriver {
     // context current; the VMM calls happen to work without one, events don't.
     if (ctx_) check(cuCtxSetCurrent_(ctx_), "cuCtxSetCurrent");
   }
-  void record_fence(void* stream) override {
-    if (!fence_) check(cuEventCreate_(&fence_, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
-    check(cuEventRecord_(fence_, static_cast<CUstream>(stream)), "cuEventRecord");
-    fence_armed_ = true;
+  // a slot is used by one thread at a time: the allocator hands it from the API thread that recorded
+  // it to the mapper thread that waits on it under its mutex
+  void record_fence(void* stream, int slot = 0) override {
+    slot &= 1;
+    if (!fence_[slot]) check(cuEventCreate_(&fence_[slot], CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+    check(cuEventRecord_(fence_[slot], static_cast<CUstream>(stream)), "cuEventRecord");
+    fence_armed_[slot] = true;
   }
-  void wait_fence() override {
-    if (fence_ && fence_armed_) {
-      check(cuEventSynchronize_(fence_), "cuEventSynchronize");
-      fence_armed_ = false;
+  void wait_fence(int slot = 0) override {
+    slot &= 1;
+    if (fence_[slot] && fence_armed_[slot]) {
+      check(cuEventSynchronize_(fence_[slot]), "cuEventSynchronize");
+      fence_armed_[slot] = false;
     }
   }
   bool is_mock() const override { return false; }
@@ -217,8 +227,8 @@ class CudaVmmDriver : public VmmDriver {
   CUcontext ctx_ = nullptr;
   CUmemAllocationProp prop_;
   CUmemAccessDesc access_;
-  CUevent fence_ = nullptr;
-  bool fence_armed_ = false;
+  CUevent fence_[2] = {nullptr, nullptr};
+  bool fence_armed_[2] = {false, false};
 
   CUresult (*cuInit_)(unsigned);
   CUresult (*cuCtxGetCurrent_)(CUcontext*);

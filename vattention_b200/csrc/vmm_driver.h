@@ -7,6 +7,7 @@
 //   MockVmmDriver  -- records calls and hands out fake VAs / handle ids; lets
 //                     the bookkeeping be checked bit-exactly on CPU.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <memory>
 #include <mutex>
@@ -47,14 +48,15 @@ class VmmDriver {
   virtual void addr_free(u64 va, u64 size) = 0;                 // cuMemAddressFree
   // make the allocator's context current on the calling thread (mapper thread)
   virtual void bind_thread() = 0;
-  // fence support: record an event on `stream` / wait for it on the host
-  virtual void record_fence(void* stream) = 0;
-  virtual void wait_fence() = 0;
+  // fence support: record an event on `stream` / wait for it on the host.  Two slots: the step that
+  // rides behind an in-flight mapper pass records into the slot that pass is not using
+  virtual void record_fence(void* stream, int slot = 0) = 0;
+  virtual void wait_fence(int slot = 0) = 0;
   virtual bool is_mock() const = 0;
-  u64 calls() const { return calls_; }
+  u64 calls() const { return calls_.load(std::memory_order_relaxed); }
 
  protected:
-  u64 calls_ = 0;
+  std::atomic<u64> calls_{0};  // the mapper thread and an API thread may both be in the driver
 };
 
 class MockVmmDriver : public VmmDriver {
@@ -69,13 +71,17 @@ class MockVmmDriver : public VmmDriver {
   void release(u64 handle) override;
   void addr_free(u64 va, u64 size) override;
   void bind_thread() override {}
-  void record_fence(void*) override {}
-  void wait_fence() override {}
+  void record_fence(void*, int slot = 0) override { fence_records_[slot & 1]++; }
+  void wait_fence(int slot = 0) override { fence_waits_[slot & 1]++; }
   bool is_mock() const override { return true; }
 
   std::vector<DriverLogRecord> snapshot_log();
   void clear_log();
   void set_capacity(u64 bytes) { capacity_ = bytes; }  // 0 = unlimited
+  // every map / set_access / unmap sleeps this long: a slow driver (eight processes in it at once)
+  void set_call_delay_us(u64 us) { delay_us_ = us; }
+  u64 fence_records(int slot) const { return fence_records_[slot & 1]; }
+  u64 fence_waits(int slot) const { return fence_waits_[slot & 1]; }
 
  private:
   void log(u64 op, u64 va, u64 size, u64 h);
@@ -83,6 +89,8 @@ class MockVmmDriver : public VmmDriver {
   u64 next_va_ = 0x7f0000000000ull;  // fake VA space, never dereferenced
   u64 next_handle_ = 1;
   u64 capacity_ = 0, in_use_ = 0;
+  std::atomic<u64> delay_us_{0};
+  std::atomic<u64> fence_records_[2] = {{0}, {0}}, fence_waits_[2] = {{0}, {0}};
   std::unordered_map<u64, u64> sizes_;
   std::mutex mu_;
   std::vector<DriverLogRecord> log_;

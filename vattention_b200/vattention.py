@@ -295,6 +295,22 @@ def clear_driver_log() -> None:
     lib.vattn_clear_driver_log(_get())
 
 
+def set_queueing(on: bool) -> None:
+    """step_async may ride behind the mapper pass in flight (default) or always wait for it (the reference)."""
+    check(lib.vattn_set_queueing(_get(), int(bool(on))))
+
+
+def mock_set_call_delay_us(us: int) -> None:
+    """HOST_MOCK: every map / set_access / unmap takes `us` microseconds."""
+    lib.vattn_mock_set_call_delay_us(_get(), int(us))
+
+
+def mock_fence_counts() -> dict:
+    out = (C.c_uint64 * 4)()
+    lib.vattn_mock_fence_counts(_get(), out)
+    return {"records": [int(out[0]), int(out[1])], "waits": [int(out[2]), int(out[3])]}
+
+
 def mock_set_capacity(nbytes: int) -> None:
     """HOST_MOCK only: physical bytes the mock device can hold (0 = unlimited)."""
     lib.vattn_mock_set_capacity(_get(), int(nbytes))
