@@ -189,6 +189,18 @@ def fp32_decode_rows(q, kc, vc, lens_after, slots, rows, scale):
 
 # ------------------------------------------------------------------------------- ours ---
 
+def crossing_schedule(batch: int, ctx: int, tpp: int, tpp_unsharded: int, warmup: int, steps: int, total_steps: int):
+    """Start lengths that make sequences cross the page boundary at `ctx` one after another during the run.
+
+    Sequence b starts off_b + 1 tokens below the boundary (plus the untimed steps before the timed
+    region), off_b spread evenly over `spread` tokens.  `spread` is a fixed FRACTION of this rank's page
+    (tokens per page grow with N as the kv heads are sharded): page crossings come ~45x more often
+    than with uniformly distributed lengths at every N -- the same token stream maps the same BYTES
+    per step on every rank count, not N times more.  Returns (spread, lengths)."""
+    spread = max(8, min(total_steps, 2 * (warmup + steps))) * (tpp // tpp_unsharded)
+    return spread, [ctx - (b * spread) // batch - 1 - (warmup + 2) for b in range(batch)]
+
+
 def run_ours(args):
     wl = workload_from(args)
     rank, local_rank, world = rank_info()
@@ -212,13 +224,7 @@ def run_ours(args):
     # every step of the run, in order: graph warm-up (2) + W + K timed + K eager (kernel timing) +
     # e2e (W + K) + parity (1)
     total_steps = 3 + W + K + K + (0 if args.no_e2e else W + K) + 2
-    # sequence b starts off_b + 1 tokens below the boundary, off_b spread evenly over `spread` tokens, so
-    # sequences cross into the next page one after another during the run.  `spread` is a fixed
-    # FRACTION of this rank's page (tokens per page grow with N as the kv heads are sharded), i.e. page
-    # crossings come ~45x more often than with uniformly distributed lengths at every N -- the same
-    # token stream maps the same BYTES per step on every rank count, not N times more.
-    spread = max(8, min(total_steps, 2 * (W + K))) * (tpp // (PAGE // (wl.hkv * D * 2)))
-    seq_lens = [CTX - (b * spread) // B - 1 - (W + 2) for b in range(B)]
+    spread, seq_lens = crossing_schedule(B, CTX, tpp, PAGE // (wl.hkv * D * 2), W, K, total_steps)
     torch.zeros(1, device=dev)                  # context for the allocator (cudaInternal.h:19-25)
     n_res = args.resident_layers
     max_ctx = CTX + tpp                          # one page of head-room past the boundary

@@ -303,3 +303,28 @@ def test_block_space_manager_accounting_against_allocator():
     finally:
         va.cleanup()
         va._use_backend(_lib.BACKEND_CUDA)
+
+
+def test_bench_crossing_schedule_is_a_fixed_fraction_of_the_page_at_every_rank_count():
+    """bench.py's start lengths: sequences cross the page boundary one after another, the window
+    they are spread over is the same fraction of a rank's page for N = 1, 2, 4, 8, and at least one
+    sequence maps a page inside the timed steps."""
+    import bench
+    page, D = 2 << 20, 128
+    for batch, hkv_full in ((64, 8), (16, 8)):
+        fractions = set()
+        for world in (1, 2, 4, 8):
+            hkv = hkv_full // world
+            tpp, tpp_full = page // (hkv * D * 2), page // (hkv_full * D * 2)
+            W, K, ctx = 3, 8, 32768
+            total = 3 + W + K + K + W + K + 2
+            spread, lens = bench.crossing_schedule(batch, ctx, tpp, tpp_full, W, K, total)
+            assert len(lens) == batch and ctx % tpp == 0
+            fractions.add(tpp / spread)
+            assert all(ctx - spread - (W + 2) - 1 <= n < ctx for n in lens)
+            # steps 1.. of the run advance every length by one; the timed steps are W + 3 .. W + 2 + K
+            crossing_steps = [ctx - n + 1 for n in lens]          # the step whose token is the page's first
+            timed = [s for s in crossing_steps if W + 3 <= s <= W + 2 + K]
+            assert timed, (batch, world, sorted(crossing_steps)[:4])
+            assert len(timed) <= max(1, -(-batch * K // spread) + 1)
+        assert len(fractions) == 1, fractions
