@@ -573,9 +573,9 @@ void KvAllocator::step_async(const u64* seq_lens, size_t n) {
     // at most one step rides behind the pass in flight
     cv_.wait(lk, [&] { return !busy_ || !queued_; });
     if (busy_ && bg_error_.empty() && can_ride_behind(seq_lens, n)) {
+      if (fence_enabled_) drv_->record_fence(compute_stream_, fence_slot_ ^ 1);  // may throw: nothing queued yet
       queued_lens_.assign(seq_lens, seq_lens + n);
       queued_ = true;
-      if (fence_enabled_) drv_->record_fence(compute_stream_, fence_slot_ ^ 1);
       stats_.sync_pages_mapped = 0;
       stats_.critical_path_ns = now_ns() - t0;
       stats_.total_critical_path_ns += stats_.critical_path_ns;
