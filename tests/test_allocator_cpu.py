@@ -583,3 +583,49 @@ def test_queued_step_records_its_fence_in_the_other_slot(mock_backend):
         assert fc["records"][0] and fc["records"][1]
     assert_same(model)
     va.mock_set_call_delay_us(0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("nodefer", [False, True])
+def test_queued_steps_with_slots_switched_by_the_length_vector(mock_backend, seed, nodefer):
+    """Slots are activated and dropped through the length vector alone (no alloc / free call in
+    between, so nothing but step_async ever meets the mapper): a step that re-activates a slot the pass
+    in flight may be taking pages from, or that needs a page nobody mapped yet, must wait; every
+    other step may ride behind.  The books must equal the oracle's at every checkpoint."""
+    L, Hkv, D, B, ctx = 2, 2, 64, 6, 32768
+    model, _ = make_pair(L, Hkv, D, B, ctx, mem_pages=4 * 14)          # 14 blocks: reclaim happens
+    if nodefer:
+        va.set_deferred_reclamation(False)
+        model.set_deferred_reclamation(False)
+    tpp = model.tokens_per_page
+    rng = random.Random(900 + seed)
+    va.mock_set_call_delay_us(120)
+    lens = [0] * B
+    for it in range(220):
+        for i in range(B):
+            r = rng.random()
+            if lens[i] == 0:
+                if r < 0.06:
+                    lens[i] = rng.choice([1, tpp - 3, tpp, tpp + 1, 2 * tpp - 2, rng.randrange(1, 3 * tpp)])
+            elif r < 0.04:
+                lens[i] = 0
+            else:
+                lens[i] = min(lens[i] + rng.choice([1, 1, 1, 1, 7]), ctx - 1)
+        err_got = err_want = None
+        try:
+            va.step_async(lens)
+        except RuntimeError as e:
+            err_got = str(e)
+        try:
+            model.step_async(lens)
+        except AllocatorOOM as e:
+            err_want = str(e)
+        assert (err_got is None) == (err_want is None), (it, err_got, err_want)
+        if err_want:
+            va.set_verbose(False)
+            big = max(range(B), key=lambda i: lens[i])
+            lens[big] = 0
+            assert_same(model)
+        elif rng.random() < 0.1:
+            assert_same(model)
+    assert_same(model)
