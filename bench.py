@@ -11,8 +11,10 @@ step_async(seq_lens) + 32 layer-calls of [flash_attn_with_kvcache(q[64,1], K, V,
 cache_seqlens, cache_batch_idx) (append + attention) -> row-parallel o_proj GEMM (+ all-reduce
 for N > 1)], producing 64 tokens.  The 32 layer-calls are replayed from a CUDA graph at every N
 (cache_seqlens is a device tensor the graph increments; step_async stays outside).  Sequence
-lengths straddle the 32K page boundary -- sequence b crosses it at a different step -- so every
-timed step makes the allocator map pages (reported: on the critical path / in the background).
+lengths straddle the 32K page boundary -- sequence b crosses it at a different step, the crossings
+spread over a fixed fraction (1/46) of the rank's page at every N -- so the timed steps make the
+allocator map pages (reported: on the critical path / in the background, the device time of every
+timed step, and how many step_async calls were queued behind a mapper pass still in flight).
 Full-model KV at this shape is 256 GiB, so (like the reference's own
 microbenchmarks/perf_pagesize/bench_pagesize.py:22) only a few layers are resident and the layer
 calls rotate over them; each call still streams its own 8.6 GB, far beyond the 126 MB L2.
