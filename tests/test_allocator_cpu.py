@@ -470,7 +470,7 @@ def test_step_async_rides_behind_a_slow_pass(mock_backend):
     # two steps after it rode behind
     assert st["queued_steps"] >= 1
     assert st["max_background_ns"] > 30e6
-    assert min(took[1:]) < 0.010, took
+    assert min(took[1:]) < 0.020, took         # (the pass it rides behind takes >= 40 ms)
     assert st["total_sync_pages"] == 2 * 2 * 4       # only the very first step mapped on the critical path
     assert_same(model)
     va.mock_set_call_delay_us(0)
